@@ -1,0 +1,158 @@
+// mm_force.cu - force / energy / virial kernels for an indexed (arbitrary) MicMec topology.
+//
+// Stands in for ForcePartMechanical._internal_compute + deformation() + _compute_gpos/_compute_vtens/_compute_epot
+// (micmec/pes/mmff.py:288-403).  Two kernels per evaluation:
+//   k_cells   one thread per cell (grid-stride): gather the 8 vertices, unwrap with the minimum-image flags
+//             (mmff.py:347-371), evaluate every metastable state + Boltzmann mixing (mm_cell.cuh), write the
+//             per-cell gradient (SoA [24][ncells]) and energy, block-reduce energy + virial with warp shuffles
+//   k_gather  one thread per node: sum the <= 8 incident per-cell gradients in the reference's fixed order
+//             j = 0..7 (mmff.py:303-318) -> deterministic, bit-reproducible; optional sum(g^2)
+//   k_final   one block: add the per-block partials in a fixed order
+// HBM traffic is dominated by the 24-double per-cell gradient (written once, read once); the structured-grid path
+// in mm_structured.cu avoids materialising it.
+#include "mm_internal.h"
+#include "mm_reduce.cuh"
+
+namespace mm {
+
+constexpr int kThreads = 128;
+
+template <int MODEL>
+__global__ void __launch_bounds__(kThreads)
+k_cells(const __grid_constant__ KParams kp, const int32_t *__restrict__ cell_nodes,
+        const uint8_t *__restrict__ cell_info, const double *__restrict__ pos, const double *__restrict__ rvecs,
+        int64_t ncells, double *__restrict__ gcell, double *__restrict__ ecell, double *__restrict__ partials) {
+    double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const double rv[9] = {rvecs[0], rvecs[1], rvecs[2], rvecs[3], rvecs[4], rvecs[5], rvecs[6], rvecs[7], rvecs[8]};
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned info = cell_info[c];
+        const int type = info & 15;
+        double R[24];
+        const int64_t n0 = cell_nodes[c];
+        const double r0x = pos[3 * n0], r0y = pos[3 * n0 + 1], r0z = pos[3 * n0 + 2];
+        R[0] = r0x;
+        R[1] = r0y;
+        R[2] = r0z;
+#pragma unroll
+        for (int v = 1; v < 8; v++) {
+            const int64_t n = cell_nodes[(int64_t)v * ncells + c];
+            // r_v = r_0 + (pos[v] - pos[0] + sum_a rvecs[a] mic[0, v, a])      mmff.py:347-371
+            const double sa = (vbit(v, 0) && (info & 16)) ? 1.0 : 0.0;
+            const double sb = (vbit(v, 1) && (info & 32)) ? 1.0 : 0.0;
+            const double sc = (vbit(v, 2) && (info & 64)) ? 1.0 : 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                double dvec = pos[3 * n + d] - R[d];
+                dvec += rv[d] * sa + rv[3 + d] * sb + rv[6 + d] * sc;
+                R[v * 3 + d] = R[d] + dvec;
+            }
+        }
+        double e, g[24], vir[6];
+        cell_eval<MODEL>(R, kp, type, e, g, vir);
+        ecell[c] = e;
+#pragma unroll
+        for (int k = 0; k < 24; k++) gcell[(int64_t)k * ncells + c] = g[k];
+        acc[0] += e;
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc[1 + k] += vir[k];
+    }
+    block_sum_store<7>(acc, partials + (size_t)blockIdx.x * kRedSlots);
+}
+
+template <bool WANT_G2>
+__global__ void __launch_bounds__(kThreads)
+k_gather(const int32_t *__restrict__ node_cells, const double *__restrict__ gcell, int64_t nnodes, int64_t ncells,
+         double *__restrict__ gpos, double *__restrict__ partials) {
+    double acc[1] = {0.0};
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nnodes; n += (int64_t)gridDim.x * blockDim.x) {
+        double gx = 0.0, gy = 0.0, gz = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int64_t c = node_cells[(int64_t)j * nnodes + n];
+            if (c >= 0) {
+                gx += gcell[(int64_t)(3 * j) * ncells + c];
+                gy += gcell[(int64_t)(3 * j + 1) * ncells + c];
+                gz += gcell[(int64_t)(3 * j + 2) * ncells + c];
+            }
+        }
+        gpos[3 * n] = gx;
+        gpos[3 * n + 1] = gy;
+        gpos[3 * n + 2] = gz;
+        if (WANT_G2) acc[0] += gx * gx + gy * gy + gz * gz;
+    }
+    if (WANT_G2) block_sum_store<1>(acc, partials + (size_t)blockIdx.x * kRedSlots);
+}
+
+__global__ void __launch_bounds__(256)
+k_final(const double *__restrict__ pc, int nbc, const double *__restrict__ pn, int nbn, ForceResult *res) {
+    double r[7];
+    partials_sum<7>(pc, nbc, kRedSlots, r);
+    double g2[1] = {0.0};
+    if (nbn > 0) partials_sum<1>(pn, nbn, kRedSlots, g2);
+    if (threadIdx.x == 0) {
+        res->epot = r[0];
+#pragma unroll
+        for (int k = 0; k < 6; k++) res->vir[k] = r[1 + k];
+        res->sum_g2 = g2[0];
+    }
+}
+
+int grid_for(const mm_handle *h, int64_t n, int threads) {
+    int64_t blocks = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)h->num_sms * 8;  // a multiple of the SM count; grid-stride loops cover the rest
+    if (blocks > cap) blocks = cap;
+    if (blocks > kMaxRedBlocks) blocks = kMaxRedBlocks;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// cell kernel only; returns the number of blocks whose partials (energy + virial) now sit in h->d_partials
+void prof_begin(mm_handle *h) {
+    if (!h->profile) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    h->prof_events.emplace_back(a, b);
+    cudaEventRecord(a, h->stream);
+}
+
+void prof_end(mm_handle *h) {
+    if (!h->profile) return;
+    cudaEventRecord(h->prof_events.back().second, h->stream);
+}
+
+int cells_launch(mm_handle *h) {
+    const int gc = grid_for(h, h->ncells, kThreads);
+    prof_begin(h);
+    if (h->model == MM_MODEL_ORIGINAL)
+        k_cells<MM_MODEL_ORIGINAL><<<gc, kThreads, 0, h->stream>>>(h->kp, h->d_cell_nodes, h->d_cell_info, h->d_pos,
+                                                                   h->d_rvecs, h->ncells, h->d_gcell, h->d_ecell,
+                                                                   h->d_partials);
+    else
+        k_cells<MM_MODEL_DEFAULT><<<gc, kThreads, 0, h->stream>>>(h->kp, h->d_cell_nodes, h->d_cell_info, h->d_pos,
+                                                                  h->d_rvecs, h->ncells, h->d_gcell, h->d_ecell,
+                                                                  h->d_partials);
+    prof_end(h);
+    h->launches++;
+    return gc;
+}
+
+int force_evaluate(mm_handle *h, double *gpos_out, bool want_g2) {
+    double *pn = h->d_partials + (size_t)kMaxRedBlocks * kRedSlots;
+    const int gc = cells_launch(h);
+    int gn = 0;
+    if (gpos_out) {
+        gn = grid_for(h, h->nnodes, kThreads);
+        if (want_g2)
+            k_gather<true><<<gn, kThreads, 0, h->stream>>>(h->d_node_cells, h->d_gcell, h->nnodes, h->ncells, gpos_out, pn);
+        else
+            k_gather<false><<<gn, kThreads, 0, h->stream>>>(h->d_node_cells, h->d_gcell, h->nnodes, h->ncells, gpos_out, pn);
+        h->launches++;
+    }
+    k_final<<<1, 256, 0, h->stream>>>(h->d_partials, gc, pn, (gpos_out && want_g2) ? gn : 0, h->d_result);
+    h->launches++;
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+
+}  // namespace mm

@@ -1,0 +1,85 @@
+// mm_internal.h - host-side structures shared by the translation units of libmicmec_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/micmec_b200.h"
+#include "mm_cell.cuh"
+
+namespace mm {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t err, const char *what);
+
+#define MM_CUDA(call)                                            \
+    do {                                                         \
+        cudaError_t err__ = (call);                              \
+        if (err__ != cudaSuccess) return mm::cuda_fail(err__, #call); \
+    } while (0)
+
+constexpr int kRedSlots = 16;        // doubles per block partial
+constexpr int kMaxRedBlocks = 2048;  // upper bound on reducing grids
+
+// Results of the last force evaluation, device resident (and mirrored to pinned host memory on request)
+struct ForceResult {
+    double epot;
+    double vir[6];   // 00,11,22,12,02,01
+    double sum_g2;   // sum of squared gradient components (rmsd_gpos), only when requested
+    double pad[8];
+};
+
+}  // namespace mm
+
+struct mm_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t nnodes = 0, ncells = 0;
+    int model = 0;
+    double boltzmann = 0.0;
+    int structured = 0;  // full periodic grid with implied topology
+    int nx = 0, ny = 0, nz = 0;
+    int num_sms = 148;
+    mm::KParams kp;
+    // indexed topology (SoA: [8][ncells] / [8][nnodes]); int32 on device
+    int32_t *d_cell_nodes = nullptr;
+    int32_t *d_node_cells = nullptr;
+    uint8_t *d_cell_info = nullptr;  // bits 0-3 type, bits 4-6 periodic wrap flags along a,b,c
+    // geometry + outputs
+    double *d_pos = nullptr;         // [nnodes][3]
+    double *d_gpos = nullptr;        // [nnodes][3]
+    double *d_gcell = nullptr;       // [24][ncells] per-cell gradients (SoA)
+    double *d_ecell = nullptr;       // [ncells]
+    double *d_partials = nullptr;    // [kMaxRedBlocks][kRedSlots]
+    mm::ForceResult *d_result = nullptr;
+    mm::ForceResult *h_result = nullptr;  // pinned
+    double *h_stage = nullptr;            // pinned staging for pos / gpos host transfers
+    size_t h_stage_bytes = 0;
+    double rvecs[9] = {0};
+    double *d_rvecs = nullptr;  // [9] device copy read by kernels (device-resident MD updates it in place)
+    int64_t launches = 0;
+    int scatter_mode = 0;
+    int profile = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // one pair per timed force-kernel launch
+    bool pos_valid = false;
+};
+
+namespace mm {
+
+// ---- mm_force.cu ------------------------------------------------------------------------------------------
+// Evaluate energy / per-cell gradients / virial partials at the positions in h->d_pos with the cell in
+// h->d_rvecs; gather node gradients into `gpos_out` (device, [nnodes][3]) when non-null; leave the reduced
+// ForceResult in h->d_result.  want_g2 additionally reduces sum(gpos^2).
+int force_evaluate(mm_handle *h, double *gpos_out, bool want_g2);
+int grid_for(const mm_handle *h, int64_t n, int threads);
+// cell kernel only; returns the number of blocks whose partials (energy + virial) were written to h->d_partials
+int cells_launch(mm_handle *h);
+// event bracket around the dominant kernel when h->profile is on
+void prof_begin(mm_handle *h);
+void prof_end(mm_handle *h);
+
+}  // namespace mm

@@ -1,0 +1,809 @@
+// mm_md.cu - device-resident velocity Verlet + Nose-Hoover chain + MTK barostat.
+//
+// Stands in for (relative to /root/reference)
+//   VerletIntegrator.initialize / propagate / compute_properties   micmec/sampling/verlet.py:119-190
+//   ConsErrTracker                                                  micmec/sampling/verlet.py:275-307
+//   NHChain.__call__ / set_ndof / get_econs_correction              micmec/sampling/nvt.py:393-458
+//   NHCThermostat.init/pre/post                                     micmec/sampling/nvt.py:507-532
+//   MTKBarostat.init/pre/post/baro/add_press_cont                   micmec/sampling/npt.py:579-757
+//   TBCombination.pre/post                                          micmec/sampling/npt.py:99-148
+//
+// Design: the whole step runs on one CUDA stream without any host round trip.  All O(1) algebra of the
+// thermostat / barostat (chain sweep, 3x3 eigen-decompositions, conserved-quantity bookkeeping) lives in a
+// single-block "scalar" kernel that reads the block partials of the node / cell kernels and updates an MDState
+// record in device memory.  Global velocity scalings and rotations are NOT applied to the velocity array when
+// the hooks ask for them: they are accumulated in a pending 3x3 matrix (MDState::Mvel) and in the algebraically
+// transformed second-moment tensor sum m v(x)v, and are applied by the next kernel that touches the
+// velocities anyway (the kick).  That removes every velocity-only pass of the reference
+// (vel *= factor, vel = vel @ rot_mat, _compute_ekin).
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "mm_internal.h"
+#include "mm_reduce.cuh"
+
+namespace mm {
+
+struct MDState {
+    double boltzmann;
+    double timestep, time, ndof;
+    long long counter, nforce;
+    // last force evaluation / kinetic moments
+    double epot, vir[6];
+    double ekin, mvv[6];  // mvv = sum m v (x) v (00,11,22,12,02,01) of the TRUE velocities
+    double sum_g2, sum_d2;
+    double rvecs[9];
+    // pending transforms
+    double Mvel[9];  // v_true = v_stored . Mvel
+    double Rpos[9];  // to be applied by k_apply_pos
+    // Nose-Hoover chain
+    int has_thermo, chain_len;
+    double ch_temp, ch_timecon;
+    double ch_pos[MM_MAX_CHAIN], ch_vel[MM_MAX_CHAIN], ch_mass[MM_MAX_CHAIN];
+    // MTK barostat
+    int has_baro, aniso, volc, baro_ndof;
+    double b_temp, b_press, b_timecon, mass_press;
+    double vp[9];
+    // conserved quantity
+    double econs_corr;
+    long long ce_n;
+    double ce_ekin_m, ce_ekin_s, ce_econs_m, ce_econs_s;
+    // properties (verlet.py:171-190)
+    double temp, etot, econs, cons_err, press, ptens[9], rmsd_gpos, rmsd_delta, volume;
+};
+
+enum : unsigned {
+    OP_RESET_MVEL = 1u << 0,
+    OP_TAKE_FORCE = 1u << 1,
+    OP_TAKE_KIN = 1u << 2,
+    OP_BARO_B = 1u << 3,
+    OP_THERMO = 1u << 4,
+    OP_BARO_A = 1u << 5,
+    OP_ECONS = 1u << 6,
+    OP_PROPS = 1u << 7,
+    OP_ADVANCE = 1u << 8,
+    OP_ZERO_VIR = 1u << 9,
+    OP_TAKE_DELTA = 1u << 10,
+    OP_SETUP = 1u << 11,
+};
+
+// ------------------------------------------------------------------------------------------- 3x3 helpers ----
+__device__ __forceinline__ void mat_mul(const double *a, const double *b, double *c) {  // c = a b (c may alias neither)
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) c[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+}
+
+__device__ __forceinline__ double volume_of(const double *r) {  // domain.c:42-48
+    return fabs(r[0] * (r[4] * r[8] - r[5] * r[7]) + r[1] * (r[5] * r[6] - r[3] * r[8]) + r[2] * (r[3] * r[7] - r[4] * r[6]));
+}
+
+// out = Q exp(scale * w) Q^T for the symmetric matrix whose lower triangle is a (numpy.linalg.eigh reads the
+// lower triangle; npt.py:686-690, 710-721).  Cyclic Jacobi, one thread.
+__device__ void sym_expm(const double *a_in, double scale, double *out) {
+    double a[3][3], q[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) a[i][j] = (i >= j) ? a_in[i * 3 + j] : a_in[j * 3 + i];
+    for (int sweep = 0; sweep < 64; sweep++) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+        if (off <= 1e-40 * (diag + 1e-300)) break;
+        for (int p = 0; p < 2; p++)
+            for (int r = p + 1; r < 3; r++) {
+                if (a[p][r] == 0.0) continue;
+                const double theta = (a[r][r] - a[p][p]) / (2.0 * a[p][r]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; k++) {
+                    const double akp = a[k][p], akr = a[k][r];
+                    a[k][p] = c * akp - s * akr;
+                    a[k][r] = s * akp + c * akr;
+                }
+                for (int k = 0; k < 3; k++) {
+                    const double apk = a[p][k], ark = a[r][k];
+                    a[p][k] = c * apk - s * ark;
+                    a[r][k] = s * apk + c * ark;
+                }
+                for (int k = 0; k < 3; k++) {
+                    const double qkp = q[k][p], qkr = q[k][r];
+                    q[k][p] = c * qkp - s * qkr;
+                    q[k][r] = s * qkp + c * qkr;
+                }
+            }
+    }
+    double f[3];
+    for (int k = 0; k < 3; k++) f[k] = exp(scale * a[k][k]);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) out[i * 3 + j] = q[i][0] * f[0] * q[j][0] + q[i][1] * f[1] * q[j][1] + q[i][2] * f[2] * q[j][2];
+}
+
+__device__ __forceinline__ void sym6_to_full(const double *s, double *m) {
+    m[0] = s[0]; m[4] = s[1]; m[8] = s[2];
+    m[5] = m[7] = s[3]; m[2] = m[6] = s[4]; m[1] = m[3] = s[5];
+}
+
+__device__ __forceinline__ void full_to_sym6(const double *m, double *s) {
+    s[0] = m[0]; s[1] = m[4]; s[2] = m[8];
+    s[3] = 0.5 * (m[5] + m[7]); s[4] = 0.5 * (m[2] + m[6]); s[5] = 0.5 * (m[1] + m[3]);
+}
+
+// ------------------------------------------------------------------------------------ scalar sub-steps -------
+__device__ double ekin_baro(const MDState &s) {  // npt.py:748-757
+    if (s.aniso) {
+        double tr = 0.0;
+        for (int i = 0; i < 9; i++) tr += s.vp[i] * s.vp[i];
+        return 0.5 * s.mass_press * tr;
+    }
+    return 0.5 * s.mass_press * s.vp[0] * s.vp[0];
+}
+
+__device__ void chain_bead(MDState &s, int k, double ekin, bool has_g1, double g1) {  // nvt.py:411-435
+    const double kb = s.boltzmann;
+    double g;
+    if (k == 0) {
+        g = 2.0 * ekin - s.ndof * s.ch_temp * kb;
+        if (has_g1) g += g1;
+    } else {
+        g = s.ch_mass[k - 1] * s.ch_vel[k - 1] * s.ch_vel[k - 1] - s.ch_temp * kb;
+    }
+    g /= s.ch_mass[k];
+    if (k == s.chain_len - 1) {
+        s.ch_vel[k] += g * s.timestep / 4.0;
+    } else {
+        s.ch_vel[k] *= exp(-s.ch_vel[k + 1] * s.timestep / 8.0);
+        s.ch_vel[k] += g * s.timestep / 4.0;
+        s.ch_vel[k] *= exp(-s.ch_vel[k + 1] * s.timestep / 8.0);
+    }
+}
+
+// NHChain.__call__ (nvt.py:410-451): the velocity scaling goes into the pending matrix and the moments
+__device__ void thermo_call(MDState &s) {
+    const bool has_g1 = s.has_baro != 0;  // TBCombination.pre/post, npt.py:107-113, 118-125
+    const double g1 = has_g1 ? 2.0 * ekin_baro(s) - s.baro_ndof * s.b_temp * s.boltzmann : 0.0;  // npt.py:738-746
+    double ekin = s.ekin;
+    for (int k = s.chain_len - 1; k >= 0; k--) chain_bead(s, k, ekin, has_g1, g1);
+    for (int k = 0; k < s.chain_len; k++) s.ch_pos[k] += s.ch_vel[k] * s.timestep / 2.0;
+    const double factor = exp(-s.ch_vel[0] * s.timestep / 2.0);
+    for (int i = 0; i < 9; i++) s.Mvel[i] *= factor;
+    for (int i = 0; i < 6; i++) s.mvv[i] *= factor * factor;
+    ekin *= factor * factor;
+    for (int k = 0; k < s.chain_len; k++) chain_bead(s, k, ekin, has_g1, g1);
+    s.ekin = ekin;
+}
+
+// update_baro_vel, npt.py:654-682
+__device__ void update_baro_vel(MDState &s) {
+    const bool has_cv0 = s.has_thermo != 0;  // TBCombination hands chain.vel[0] to the barostat, npt.py:102-106
+    const double damp = has_cv0 ? exp(-s.timestep * s.ch_vel[0] / 8.0) : 1.0;
+    const int nvp = s.aniso ? 9 : 1;
+    if (has_cv0)
+        for (int i = 0; i < nvp; i++) s.vp[i] *= damp;
+    double G[9], pv[6];
+    for (int i = 0; i < 6; i++) pv[i] = s.mvv[i] - s.vir[i];  // both symmetric here: 0.5 (pv^T + pv) is a no-op
+    sym6_to_full(pv, G);
+    const double iso = 2.0 * s.ekin / s.ndof - s.b_press * volume_of(s.rvecs);
+    for (int i = 0; i < 9; i++) G[i] = (G[i] + ((i % 4 == 0) ? iso : 0.0)) / s.mass_press;
+    if (!s.aniso) {
+        s.vp[0] += (G[0] + G[4] + G[8]) * s.timestep / 4.0;
+    } else {
+        if (s.volc) {
+            const double tr = (G[0] + G[4] + G[8]) / 3.0;
+            G[0] -= tr; G[4] -= tr; G[8] -= tr;
+        }
+        for (int i = 0; i < 9; i++) s.vp[i] += G[i] * s.timestep / 4.0;
+    }
+    if (has_cv0)
+        for (int i = 0; i < nvp; i++) s.vp[i] *= damp;
+}
+
+// first half of MTKBarostat.baro (npt.py:683-700): barostat velocity, position/cell rotation
+__device__ void baro_a(MDState &s) {
+    update_baro_vel(s);
+    if (s.aniso) {
+        sym_expm(s.vp, s.timestep / 2.0, s.Rpos);
+    } else {
+        const double c = exp(s.vp[0] * s.timestep / 2.0);
+        for (int i = 0; i < 9; i++) s.Rpos[i] = (i % 4 == 0) ? c : 0.0;
+    }
+    double nr[9];
+    mat_mul(s.rvecs, s.Rpos, nr);
+    for (int i = 0; i < 9; i++) s.rvecs[i] = nr[i];
+}
+
+// second half of MTKBarostat.baro (npt.py:708-736): velocity rotation (deferred), kinetic energy, barostat velocity
+__device__ void baro_b(MDState &s) {
+    double R[9];
+    if (s.aniso) {
+        double A[9];
+        for (int i = 0; i < 9; i++) A[i] = s.vp[i];
+        if (!s.volc) {
+            const double tr = (A[0] + A[4] + A[8]) / s.ndof;
+            A[0] += tr; A[4] += tr; A[8] += tr;
+        }
+        sym_expm(A, -s.timestep / 2.0, R);
+    } else {
+        const double c = exp(-((1.0 + 3.0 / s.ndof) * s.vp[0]) * s.timestep / 2.0);
+        for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? c : 0.0;
+    }
+    double t[9], m[9], mt[9];
+    mat_mul(s.Mvel, R, t);
+    for (int i = 0; i < 9; i++) s.Mvel[i] = t[i];
+    // sum m (vR)(x)(vR) = R^T (sum m v(x)v) R
+    sym6_to_full(s.mvv, m);
+    mat_mul(m, R, mt);
+    double Rt[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) Rt[i * 3 + j] = R[j * 3 + i];
+    mat_mul(Rt, mt, m);
+    full_to_sym6(m, s.mvv);
+    s.ekin = 0.5 * (s.mvv[0] + s.mvv[1] + s.mvv[2]);
+    update_baro_vel(s);
+}
+
+__device__ void econs_update(MDState &s) {
+    double corr = 0.0;
+    const double kb = s.boltzmann;
+    if (s.has_thermo) {  // nvt.py:453-458
+        const double kt = kb * s.ch_temp;
+        double a = 0.0, p = 0.0;
+        for (int k = 0; k < s.chain_len; k++) a += s.ch_vel[k] * s.ch_vel[k] * s.ch_mass[k];
+        for (int k = 1; k < s.chain_len; k++) p += s.ch_pos[k];
+        corr += 0.5 * a + kt * (s.ndof * s.ch_pos[0] + p);
+    }
+    if (s.has_baro) {  // npt.py:644-651, 134-148
+        corr += ekin_baro(s);
+        if (!s.volc) corr += s.b_press * volume_of(s.rvecs);
+        if (s.has_thermo) corr += s.baro_ndof * kb * s.ch_temp * s.ch_pos[0];
+    }
+    s.econs_corr = corr;
+}
+
+__device__ void properties(MDState &s, double n3) {  // verlet.py:171-190
+    s.rmsd_gpos = sqrt(s.sum_g2 / n3);
+    s.rmsd_delta = sqrt(s.sum_d2 / n3);
+    s.temp = (s.ekin / s.ndof) * (2.0 / s.boltzmann);
+    s.etot = s.ekin + s.epot;
+    s.econs = s.etot + s.econs_corr;
+    if (s.ce_n == 0) {  // verlet.py:289-307
+        s.ce_ekin_m = s.ekin;
+        s.ce_econs_m = s.econs;
+    } else {
+        double t = s.ekin - s.ce_ekin_m;
+        s.ce_ekin_m += t / (double)(s.ce_n + 1);
+        s.ce_ekin_s += t * (s.ekin - s.ce_ekin_m);
+        t = s.econs - s.ce_econs_m;
+        s.ce_econs_m += t / (double)(s.ce_n + 1);
+        s.ce_econs_s += t * (s.econs - s.ce_econs_m);
+    }
+    s.ce_n++;
+    s.cons_err = (s.ce_n > 1) ? sqrt(s.ce_econs_s / s.ce_ekin_s) : 0.0;
+    s.volume = volume_of(s.rvecs);
+    double m[9], v[9];
+    sym6_to_full(s.mvv, m);
+    sym6_to_full(s.vir, v);
+    if (s.volume > 0.0) {  // verlet.py:185: only for periodic systems
+        for (int i = 0; i < 9; i++) s.ptens[i] = (m[i] - v[i]) / s.volume;
+        s.press = (s.ptens[0] + s.ptens[4] + s.ptens[8]) / 3.0;
+    }
+}
+
+// One block.  Sums the block partials it is told to consume, then thread 0 runs the requested sub-steps in the
+// canonical order RESET_MVEL, TAKE_FORCE, TAKE_KIN, BARO_B, THERMO, BARO_A, ECONS, PROPS (see md_step below).
+__global__ void __launch_bounds__(256)
+k_scalar(MDState *st, double *rvecs_dev, unsigned ops, const double *pc, int nbc, const double *pn, int nbn,
+         const double *pd, int nbd, double n3) {
+    double fr[7] = {0, 0, 0, 0, 0, 0, 0}, kn[7] = {0, 0, 0, 0, 0, 0, 0}, dl[1] = {0};
+    if (ops & OP_TAKE_FORCE) partials_sum<7>(pc, nbc, kRedSlots, fr);
+    if ((ops & (OP_TAKE_KIN | OP_TAKE_FORCE)) && nbn > 0) partials_sum<7>(pn, nbn, kRedSlots, kn);
+    if ((ops & OP_TAKE_DELTA) && nbd > 0) partials_sum<1>(pd, nbd, kRedSlots, dl);
+    if (threadIdx.x != 0) return;
+    MDState &s = *st;
+    if (ops & OP_RESET_MVEL)
+        for (int i = 0; i < 9; i++) s.Mvel[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (ops & OP_TAKE_FORCE) {
+        s.epot = fr[0];
+        for (int k = 0; k < 6; k++) s.vir[k] = fr[1 + k];
+        if (nbn > 0) s.sum_g2 = kn[6];
+        s.nforce++;
+    }
+    if (ops & OP_ZERO_VIR)  // verlet.py:124 passes no vtens to the first compute: it stays zero
+        for (int k = 0; k < 6; k++) s.vir[k] = 0.0;
+    if (ops & OP_TAKE_KIN) {
+        for (int k = 0; k < 6; k++) s.mvv[k] = kn[k];
+        s.ekin = 0.5 * (kn[0] + kn[1] + kn[2]);
+    }
+    if (ops & OP_TAKE_DELTA) s.sum_d2 = dl[0];
+    if (ops & OP_SETUP) {  // nvt.py:393-400, npt.py:591-596, verlet.py:131-132, sampling/utils.py:340-343
+        if ((s.has_thermo || s.has_baro) && s.ndof <= 0.0) s.ndof = n3 - 3.0;
+        if (s.ndof <= 0.0) s.ndof = n3;
+        if (s.has_thermo) {
+            const double afreq = 2.0 * M_PI / s.ch_timecon;
+            for (int k = 0; k < s.chain_len; k++) s.ch_mass[k] = s.boltzmann * s.ch_temp / (afreq * afreq);
+            s.ch_mass[0] *= s.ndof;
+        }
+        if (s.has_baro) {
+            const double angfreq = 2.0 * M_PI / s.b_timecon;
+            s.mass_press = (s.ndof + 9.0) * s.boltzmann * s.b_temp / (angfreq * angfreq);
+            if (s.volc) {  // npt.py:606-608
+                const double tr = (s.vp[0] + s.vp[4] + s.vp[8]) / 3.0;
+                s.vp[0] -= tr; s.vp[4] -= tr; s.vp[8] -= tr;
+            }
+        }
+    }
+    if (ops & OP_BARO_B) baro_b(s);
+    if (ops & OP_THERMO) thermo_call(s);
+    if (ops & OP_BARO_A) {
+        baro_a(s);
+        for (int i = 0; i < 9; i++) rvecs_dev[i] = s.rvecs[i];
+    }
+    if (ops & OP_ECONS) econs_update(s);
+    if (ops & OP_ADVANCE) {
+        s.time += s.timestep;
+        s.counter++;
+    }
+    if (ops & OP_PROPS) properties(s, n3);
+}
+
+// --------------------------------------------------------------------------------------- node kernels --------
+constexpr int kNodeThreads = 256;
+
+// v <- v.Mvel - (dt/2) g/m ; x <- x + dt v      (hook scalings + verlet.py:144-146); optional posold snapshot
+__global__ void __launch_bounds__(kNodeThreads)
+k_kick_drift(const MDState *__restrict__ st, double *__restrict__ pos, double *__restrict__ vel,
+             const double *__restrict__ gpos, const double *__restrict__ masses, double *__restrict__ posold, int64_t n) {
+    double M[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) M[i] = st->Mvel[i];
+    const double dt = st->timestep;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+        const double im = 1.0 / masses[i];
+        double w[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const double vt = vx * M[j] + vy * M[3 + j] + vz * M[6 + j];
+            const double acc = -gpos[3 * i + j] * im;
+            w[j] = vt + 0.5 * acc * dt;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const double x = pos[3 * i + j];
+            if (posold) posold[3 * i + j] = x;
+            pos[3 * i + j] = x + dt * w[j];
+            vel[3 * i + j] = w[j];
+        }
+    }
+}
+
+// gather the node gradient (mmff.py:303-318), second kick (verlet.py:152-153), kinetic moments + sum g^2
+__global__ void __launch_bounds__(kNodeThreads)
+k_gather_kick2(const MDState *__restrict__ st, const int32_t *__restrict__ node_cells, const double *__restrict__ gcell,
+               int64_t nnodes, int64_t ncells, double *__restrict__ gpos, double *__restrict__ vel,
+               const double *__restrict__ masses, double *__restrict__ partials) {
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const double dt = st->timestep;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nnodes; n += (int64_t)gridDim.x * blockDim.x) {
+        double g[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int64_t c = node_cells[(int64_t)j * nnodes + n];
+            if (c >= 0) {
+                g[0] += gcell[(int64_t)(3 * j) * ncells + c];
+                g[1] += gcell[(int64_t)(3 * j + 1) * ncells + c];
+                g[2] += gcell[(int64_t)(3 * j + 2) * ncells + c];
+            }
+        }
+        const double m = masses[n], im = 1.0 / m;
+        double v[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            gpos[3 * n + j] = g[j];
+            const double a = -g[j] * im;
+            v[j] = vel[3 * n + j] + 0.5 * a * dt;
+            vel[3 * n + j] = v[j];
+        }
+        acc[0] += m * v[0] * v[0];
+        acc[1] += m * v[1] * v[1];
+        acc[2] += m * v[2] * v[2];
+        acc[3] += m * v[1] * v[2];
+        acc[4] += m * v[0] * v[2];
+        acc[5] += m * v[0] * v[1];
+        acc[6] += g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+    }
+    block_sum_store<7>(acc, partials + (size_t)blockIdx.x * kRedSlots);
+}
+
+// gradient gather without kick (barostat force calls, npt.py:702-707) + sum g^2 in slot 6
+__global__ void __launch_bounds__(kNodeThreads)
+k_gather_g2(const int32_t *__restrict__ node_cells, const double *__restrict__ gcell, int64_t nnodes, int64_t ncells,
+            double *__restrict__ gpos, double *__restrict__ partials) {
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < nnodes; n += (int64_t)gridDim.x * blockDim.x) {
+        double g[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int64_t c = node_cells[(int64_t)j * nnodes + n];
+            if (c >= 0) {
+                g[0] += gcell[(int64_t)(3 * j) * ncells + c];
+                g[1] += gcell[(int64_t)(3 * j + 1) * ncells + c];
+                g[2] += gcell[(int64_t)(3 * j + 2) * ncells + c];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) gpos[3 * n + j] = g[j];
+        acc[6] += g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+    }
+    block_sum_store<7>(acc, partials + (size_t)blockIdx.x * kRedSlots);
+}
+
+// kinetic moments of the stored velocities (initialisation)
+__global__ void __launch_bounds__(kNodeThreads)
+k_moments(const double *__restrict__ vel, const double *__restrict__ masses, const double *__restrict__ gpos, int64_t n,
+          double *__restrict__ partials) {
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double m = masses[i], vx = vel[3 * i], vy = vel[3 * i + 1], vz = vel[3 * i + 2];
+        acc[0] += m * vx * vx;
+        acc[1] += m * vy * vy;
+        acc[2] += m * vz * vz;
+        acc[3] += m * vy * vz;
+        acc[4] += m * vx * vz;
+        acc[5] += m * vx * vy;
+        acc[6] += gpos[3 * i] * gpos[3 * i] + gpos[3 * i + 1] * gpos[3 * i + 1] + gpos[3 * i + 2] * gpos[3 * i + 2];
+    }
+    block_sum_store<7>(acc, partials + (size_t)blockIdx.x * kRedSlots);
+}
+
+// x <- x.Rpos (npt.py:689-698); optional posold snapshot of the un-rotated positions
+__global__ void __launch_bounds__(kNodeThreads)
+k_apply_pos(const MDState *__restrict__ st, double *__restrict__ pos, double *__restrict__ posold, int64_t n) {
+    double R[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) R[i] = st->Rpos[i];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+        if (posold) {
+            posold[3 * i] = x;
+            posold[3 * i + 1] = y;
+            posold[3 * i + 2] = z;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) pos[3 * i + j] = x * R[j] + y * R[3 + j] + z * R[6 + j];
+    }
+}
+
+// v <- v.Mvel : make the stored velocities the true ones (before a state read-back)
+__global__ void __launch_bounds__(kNodeThreads)
+k_flush_vel(const MDState *__restrict__ st, double *__restrict__ vel, int64_t n) {
+    double M[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) M[i] = st->Mvel[i];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = vel[3 * i], y = vel[3 * i + 1], z = vel[3 * i + 2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) vel[3 * i + j] = x * M[j] + y * M[3 + j] + z * M[6 + j];
+    }
+}
+
+// sum (pos - posold)^2  (verlet.py:158-161, 173)
+__global__ void __launch_bounds__(kNodeThreads)
+k_delta(const double *__restrict__ pos, const double *__restrict__ posold, int64_t n3, double *__restrict__ partials) {
+    double acc[1] = {0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (int64_t)gridDim.x * blockDim.x) {
+        const double d = pos[i] - posold[i];
+        acc[0] += d * d;
+    }
+    block_sum_store<1>(acc, partials + (size_t)blockIdx.x * kRedSlots);
+}
+
+}  // namespace mm
+
+using namespace mm;
+
+struct mm_md {
+    mm_handle *h = nullptr;
+    mm_md_desc desc;
+    MDState *d_state = nullptr;
+    MDState *h_state = nullptr;  // pinned mirror
+    double *d_vel = nullptr, *d_masses = nullptr, *d_posold = nullptr;
+    double *d_pkin = nullptr;    // partials of node kernels [kMaxRedBlocks][kRedSlots]
+    double *d_pdelta = nullptr;  // partials of k_delta
+    bool initialised = false;
+};
+
+namespace mm {
+
+static int scalar_launch(mm_md *md, unsigned ops, int nbc, int nbn, int nbd) {
+    mm_handle *h = md->h;
+    k_scalar<<<1, 256, 0, h->stream>>>(md->d_state, h->d_rvecs, ops, h->d_partials, nbc, md->d_pkin, nbn, md->d_pdelta,
+                                       nbd, 3.0 * (double)h->nnodes);
+    h->launches++;
+    return MM_OK;
+}
+
+// one barostat force call: x <- x.Rpos, cells, gather (npt.py:683-707)
+static int baro_force(mm_md *md, bool snapshot, int &nbc, int &nbn) {
+    mm_handle *h = md->h;
+    const int gn = grid_for(h, h->nnodes, kNodeThreads);
+    k_apply_pos<<<gn, kNodeThreads, 0, h->stream>>>(md->d_state, h->d_pos, snapshot ? md->d_posold : nullptr, h->nnodes);
+    h->launches++;
+    nbc = cells_launch(h);
+    k_gather_g2<<<gn, kNodeThreads, 0, h->stream>>>(h->d_node_cells, h->d_gcell, h->nnodes, h->ncells, h->d_gpos, md->d_pkin);
+    h->launches++;
+    nbn = gn;
+    return MM_OK;
+}
+
+// VerletIntegrator.propagate (verlet.py:140-166).  `full` additionally produces rmsd_delta for this step.
+static int md_step(mm_md *md, bool full) {
+    mm_handle *h = md->h;
+    const bool thermo = md->desc.has_thermo != 0, baro = md->desc.has_baro != 0;
+    const int gn = grid_for(h, h->nnodes, kNodeThreads);
+    int nbc = 0, nbn = 0;
+    // ---- "pre" hooks: TBCombination.pre = barostat, then thermostat (npt.py:99-115) ----
+    if (baro) {
+        scalar_launch(md, OP_BARO_A, 0, 0, 0);
+        baro_force(md, full, nbc, nbn);
+        scalar_launch(md, OP_TAKE_FORCE | OP_BARO_B | (thermo ? OP_THERMO : 0u), nbc, nbn, 0);
+    } else if (thermo) {
+        scalar_launch(md, OP_THERMO, 0, 0, 0);
+    }
+    // ---- velocity Verlet (verlet.py:144-154) ----
+    k_kick_drift<<<gn, kNodeThreads, 0, h->stream>>>(md->d_state, h->d_pos, md->d_vel, h->d_gpos, md->d_masses,
+                                                     (full && !baro) ? md->d_posold : nullptr, h->nnodes);
+    h->launches++;
+    nbc = cells_launch(h);
+    k_gather_kick2<<<gn, kNodeThreads, 0, h->stream>>>(md->d_state, h->d_node_cells, h->d_gcell, h->nnodes, h->ncells,
+                                                       h->d_gpos, md->d_vel, md->d_masses, md->d_pkin);
+    h->launches++;
+    // ---- "post" hooks: thermostat, then barostat (npt.py:117-148), then verlet.py:158-166 ----
+    unsigned ops = OP_RESET_MVEL | OP_TAKE_FORCE | OP_TAKE_KIN | (thermo ? OP_THERMO : 0u);
+    int nbd = 0;
+    if (!baro) {
+        if (full) {
+            nbd = grid_for(h, 3 * h->nnodes, kNodeThreads);
+            k_delta<<<nbd, kNodeThreads, 0, h->stream>>>(h->d_pos, md->d_posold, 3 * h->nnodes, md->d_pdelta);
+            h->launches++;
+            ops |= OP_TAKE_DELTA;
+        }
+        scalar_launch(md, ops | OP_ECONS | OP_ADVANCE | OP_PROPS, nbc, gn, nbd);
+    } else {
+        scalar_launch(md, ops | OP_BARO_A, nbc, gn, 0);
+        baro_force(md, false, nbc, nbn);
+        ops = OP_TAKE_FORCE | OP_BARO_B | OP_ECONS | OP_ADVANCE | OP_PROPS;
+        if (full) {
+            nbd = grid_for(h, 3 * h->nnodes, kNodeThreads);
+            k_delta<<<nbd, kNodeThreads, 0, h->stream>>>(h->d_pos, md->d_posold, 3 * h->nnodes, md->d_pdelta);
+            h->launches++;
+            ops |= OP_TAKE_DELTA;
+        }
+        scalar_launch(md, ops, nbc, nbn, nbd);
+    }
+    return MM_OK;
+}
+
+}  // namespace mm
+
+extern "C" {
+
+int mm_md_destroy(mm_md *md) {
+    if (!md) return MM_OK;
+    cudaSetDevice(md->h->device);
+    cudaFree(md->d_state);
+    cudaFree(md->d_vel);
+    cudaFree(md->d_masses);
+    cudaFree(md->d_posold);
+    cudaFree(md->d_pkin);
+    cudaFree(md->d_pdelta);
+    if (md->h_state) cudaFreeHost(md->h_state);
+    delete md;
+    return MM_OK;
+}
+
+int mm_md_create(mm_handle *h, const mm_md_desc *desc, mm_md **out) {
+    if (!h || !desc || !out) {
+        set_error("mm_md_create: null argument");
+        return MM_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (desc->has_thermo && (desc->chain_length < 1 || desc->chain_length > MM_MAX_CHAIN)) {
+        set_error("mm_md_create: unsupported Nose-Hoover chain length");
+        return MM_ERR_INVALID;
+    }
+    if (desc->has_baro && !desc->anisotropic && desc->vol_constraint) {
+        set_error("Isotropic barostat called with a volume constraint.");  // sampling/utils.py:499-500
+        return MM_ERR_INVALID;
+    }
+    if (!(desc->timestep > 0.0)) {
+        set_error("mm_md_create: timestep must be positive");
+        return MM_ERR_INVALID;
+    }
+    mm_md *md = new (std::nothrow) mm_md();
+    if (!md) return MM_ERR_INVALID;
+    md->h = h;
+    md->desc = *desc;
+    const int64_t nn = h->nnodes;
+#define MM_TRY(call)                                \
+    do {                                            \
+        cudaError_t err__ = (call);                 \
+        if (err__ != cudaSuccess) {                 \
+            int rc__ = mm::cuda_fail(err__, #call); \
+            mm_md_destroy(md);                      \
+            return rc__;                            \
+        }                                           \
+    } while (0)
+    MM_TRY(cudaSetDevice(h->device));
+    MM_TRY(cudaMalloc(&md->d_state, sizeof(MDState)));
+    MM_TRY(cudaMalloc(&md->d_vel, sizeof(double) * 3 * nn));
+    MM_TRY(cudaMalloc(&md->d_masses, sizeof(double) * nn));
+    MM_TRY(cudaMalloc(&md->d_posold, sizeof(double) * 3 * nn));
+    MM_TRY(cudaMalloc(&md->d_pkin, sizeof(double) * kMaxRedBlocks * kRedSlots));
+    MM_TRY(cudaMalloc(&md->d_pdelta, sizeof(double) * kMaxRedBlocks * kRedSlots));
+    MM_TRY(cudaHostAlloc(&md->h_state, sizeof(MDState), cudaHostAllocDefault));
+#undef MM_TRY
+    *out = md;
+    return MM_OK;
+}
+
+int mm_md_init(mm_md *md, const double *pos, const double *vel, const double *masses, int where, const double *rvecs9,
+               const double *chain_pos, const double *chain_vel, const double *vel_press9) {
+    if (!md || !pos || !vel || !masses || !rvecs9) {
+        set_error("mm_md_init: null argument");
+        return MM_ERR_INVALID;
+    }
+    mm_handle *h = md->h;
+    const int64_t nn = h->nnodes;
+    MM_CUDA(cudaSetDevice(h->device));
+    const cudaMemcpyKind kind = where == MM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    int rc = mm_set_pos(h, pos, where);
+    if (rc != MM_OK) return rc;
+    rc = mm_set_rvecs(h, rvecs9);
+    if (rc != MM_OK) return rc;
+    MM_CUDA(cudaMemcpyAsync(md->d_vel, vel, sizeof(double) * 3 * nn, kind, h->stream));
+    MM_CUDA(cudaMemcpyAsync(md->d_masses, masses, sizeof(double) * nn, kind, h->stream));
+    MM_CUDA(cudaMemsetAsync(md->d_posold, 0, sizeof(double) * 3 * nn, h->stream));
+    MDState &s = *md->h_state;
+    memset(&s, 0, sizeof(s));
+    const mm_md_desc &d = md->desc;
+    s.boltzmann = h->boltzmann;
+    s.timestep = d.timestep;
+    s.ndof = d.ndof;
+    for (int i = 0; i < 9; i++) {
+        s.rvecs[i] = rvecs9[i];
+        s.Mvel[i] = s.Rpos[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    }
+    s.has_thermo = d.has_thermo;
+    s.chain_len = d.has_thermo ? d.chain_length : 0;
+    s.ch_temp = d.thermo_temp;
+    s.ch_timecon = d.thermo_timecon;
+    for (int k = 0; k < s.chain_len; k++) {
+        s.ch_pos[k] = chain_pos ? chain_pos[k] : 0.0;
+        s.ch_vel[k] = chain_vel ? chain_vel[k] : 0.0;
+    }
+    s.has_baro = d.has_baro;
+    s.aniso = d.anisotropic;
+    s.volc = d.vol_constraint;
+    s.baro_ndof = (d.anisotropic ? 6 : 1) - (d.vol_constraint ? 1 : 0);  // sampling/utils.py:478-501
+    s.b_temp = d.baro_temp;
+    s.b_press = d.baro_press;
+    s.b_timecon = d.baro_timecon;
+    if (d.has_baro && vel_press9)
+        for (int i = 0; i < (d.anisotropic ? 9 : 1); i++) s.vp[i] = vel_press9[i];
+    MM_CUDA(cudaMemcpyAsync(md->d_state, md->h_state, sizeof(MDState), cudaMemcpyHostToDevice, h->stream));
+    // verlet.py:119-137: first force evaluation (no vtens unless a barostat re-evaluates, npt.py:612-614)
+    const int gn = grid_for(h, nn, kNodeThreads);
+    const int nbc = cells_launch(h);
+    k_gather_g2<<<gn, kNodeThreads, 0, h->stream>>>(h->d_node_cells, h->d_gcell, nn, h->ncells, h->d_gpos, md->d_pkin);
+    h->launches++;
+    scalar_launch(md, OP_TAKE_FORCE | (d.has_baro ? 0u : OP_ZERO_VIR) | OP_SETUP, nbc, gn, 0);
+    // (with a barostat the reference evaluates the same geometry a second time, now with vtens, npt.py:612-614;
+    //  the virial of the first evaluation is kept here instead)
+    k_moments<<<gn, kNodeThreads, 0, h->stream>>>(md->d_vel, md->d_masses, h->d_gpos, nn, md->d_pkin);
+    h->launches++;
+    scalar_launch(md, OP_TAKE_KIN | OP_PROPS, 0, gn, 0);
+    MM_CUDA(cudaGetLastError());
+    MM_CUDA(cudaStreamSynchronize(h->stream));
+    md->initialised = true;
+    return MM_OK;
+}
+
+int mm_md_set_state(mm_md *md, const double *pos, const double *vel, int where) {
+    if (!md || !md->initialised) {
+        set_error("mm_md_set_state: integrator not initialised");
+        return MM_ERR_STATE;
+    }
+    mm_handle *h = md->h;
+    MM_CUDA(cudaSetDevice(h->device));
+    const cudaMemcpyKind kind = where == MM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (pos) MM_CUDA(cudaMemcpyAsync(h->d_pos, pos, sizeof(double) * 3 * h->nnodes, kind, h->stream));
+    if (vel) {
+        // the uploaded velocities are the true ones: drop any pending transform
+        scalar_launch(md, OP_RESET_MVEL, 0, 0, 0);
+        MM_CUDA(cudaMemcpyAsync(md->d_vel, vel, sizeof(double) * 3 * h->nnodes, kind, h->stream));
+    }
+    return MM_OK;
+}
+
+int mm_md_run(mm_md *md, int64_t nsteps) {
+    if (!md || !md->initialised) {
+        set_error("mm_md_run: integrator not initialised");
+        return MM_ERR_STATE;
+    }
+    MM_CUDA(cudaSetDevice(md->h->device));
+    for (int64_t i = 0; i < nsteps; i++) md_step(md, i == nsteps - 1);
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+
+int mm_md_get_state(mm_md *md, double *pos, double *vel, double *gpos, int where, double *rvecs9, double *chain_pos,
+                    double *chain_vel, double *vel_press9) {
+    if (!md || !md->initialised) {
+        set_error("mm_md_get_state: integrator not initialised");
+        return MM_ERR_STATE;
+    }
+    mm_handle *h = md->h;
+    const int64_t nn = h->nnodes;
+    MM_CUDA(cudaSetDevice(h->device));
+    const cudaMemcpyKind kind = where == MM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (vel) {
+        const int gn = grid_for(h, nn, kNodeThreads);
+        k_flush_vel<<<gn, kNodeThreads, 0, h->stream>>>(md->d_state, md->d_vel, nn);
+        h->launches++;
+        scalar_launch(md, OP_RESET_MVEL, 0, 0, 0);
+        MM_CUDA(cudaMemcpyAsync(vel, md->d_vel, sizeof(double) * 3 * nn, kind, h->stream));
+    }
+    if (pos) MM_CUDA(cudaMemcpyAsync(pos, h->d_pos, sizeof(double) * 3 * nn, kind, h->stream));
+    if (gpos) MM_CUDA(cudaMemcpyAsync(gpos, h->d_gpos, sizeof(double) * 3 * nn, kind, h->stream));
+    MM_CUDA(cudaMemcpyAsync(md->h_state, md->d_state, sizeof(MDState), cudaMemcpyDeviceToHost, h->stream));
+    MM_CUDA(cudaStreamSynchronize(h->stream));
+    const MDState &s = *md->h_state;
+    memcpy(h->rvecs, s.rvecs, sizeof(double) * 9);
+    if (rvecs9) memcpy(rvecs9, s.rvecs, sizeof(double) * 9);
+    if (chain_pos) memcpy(chain_pos, s.ch_pos, sizeof(double) * s.chain_len);
+    if (chain_vel) memcpy(chain_vel, s.ch_vel, sizeof(double) * s.chain_len);
+    if (vel_press9) memcpy(vel_press9, s.vp, sizeof(double) * 9);
+    return MM_OK;
+}
+
+int mm_md_scalars(mm_md *md, double *out) {
+    if (!md || !md->initialised || !out) {
+        set_error("mm_md_scalars: integrator not initialised");
+        return MM_ERR_STATE;
+    }
+    mm_handle *h = md->h;
+    MM_CUDA(cudaSetDevice(h->device));
+    MM_CUDA(cudaMemcpyAsync(md->h_state, md->d_state, sizeof(MDState), cudaMemcpyDeviceToHost, h->stream));
+    MM_CUDA(cudaStreamSynchronize(h->stream));
+    const MDState &s = *md->h_state;
+    for (int i = 0; i < MM_S_COUNT; i++) out[i] = 0.0;
+    out[MM_S_EPOT] = s.epot;
+    out[MM_S_EKIN] = s.ekin;
+    out[MM_S_TEMP] = s.temp;
+    out[MM_S_ETOT] = s.etot;
+    out[MM_S_ECONS] = s.econs;
+    out[MM_S_CONS_ERR] = s.cons_err;
+    out[MM_S_PRESS] = s.press;
+    out[MM_S_RMSD_GPOS] = s.rmsd_gpos;
+    out[MM_S_RMSD_DELTA] = s.rmsd_delta;
+    out[MM_S_TIME] = s.time;
+    out[MM_S_COUNTER] = (double)s.counter;
+    out[MM_S_VOLUME] = s.volume;
+    out[MM_S_NDOF] = s.ndof;
+    out[MM_S_ECONS_CORR] = s.econs_corr;
+    double v[9];
+    v[0] = s.vir[0]; v[4] = s.vir[1]; v[8] = s.vir[2];
+    v[5] = v[7] = s.vir[3]; v[2] = v[6] = s.vir[4]; v[1] = v[3] = s.vir[5];
+    for (int i = 0; i < 9; i++) {
+        out[MM_S_VTENS + i] = v[i];
+        out[MM_S_PTENS + i] = s.ptens[i];
+    }
+    out[MM_S_NFORCE] = (double)s.nforce;
+    // the reference raises from inside compute() (mmff.py:135-147); here the flag surfaces with the scalars
+    if (std::isnan(s.epot) || std::isnan(s.ekin)) {
+        set_error("The energy is not-a-number (``nan``).");
+        return MM_ERR_NAN;
+    }
+    return MM_OK;
+}
+
+}  // extern "C"
