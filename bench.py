@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the MicMec force + integration hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--grid G] [--ensemble npt|nvt|nve] [--impl ours|reference]
+
+Metric (BASELINE.json): MD node-steps/s (force + Verlet, fp64).  A "step" is one VerletIntegrator.propagate of the
+synthetic G^3-cell periodic fcu grid (default 256^3, NPT = NHC thermostat + MTK barostat = 3 force evaluations per
+step, BASELINE.json configs[3]).  One JSON line is printed by rank 0.
+
+`value`        device-resident loop (mm_md_run), state already in HBM, CUDA events on the launching stream
+`e2e`          the same step driven through the C ABI with HOST buffers: pinned-host pos+vel uploaded, one step,
+               pos+vel+scalars read back, every step
+`roofline`     dominant kernel (the per-cell force kernel): algorithmic bytes / measured launch time vs the measured
+               HBM copy bandwidth in MEASURED_PEAKS.json
+`cpu_baseline` the CPU oracle port (oracle/micmec_oracle.c, OpenMP) timed on the box's host cores on a bounded sample
+`--impl reference` times that CPU port alone, with all host threads, on the same metric.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_NODE_STEP = 108.0   # pos r/w 48 + vel r/w 48 + mass 8 + cell type 4, per force-evaluation-step
+BYTES_PER_NODE_EVAL = 52.0    # force-only evaluation: pos 24 + type 4 + gpos 24
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--ensemble", default="npt", choices=["nve", "nvt", "npt"])
+    ap.add_argument("--model", default="original", choices=["original", "default"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-grid", type=int, default=48, help="edge of the bounded CPU sample grid")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+FORCE_EVALS = {"nve": 1, "nvt": 1, "npt": 3}
+
+
+def make_state(grid, seed=0, amp=0.1):
+    """Synthetic G^3 fcu grid: rest lattice + `amp` bohr Gaussian displacement, Maxwell-Boltzmann velocities at
+    300 K with the centre-of-mass motion removed (same recipe as sampling/utils.get_random_vel, seeded)."""
+    from micmec_b200.system import System
+    from micmec_b200.celltypes import TYPE_FCU
+    from micmec_b200.units import boltzmann
+
+    system = System.periodic_grid((grid,) * 3, TYPE_FCU, explicit=grid <= 64)
+    rng = np.random.default_rng(seed)
+    system.pos += amp * rng.standard_normal(system.pos.shape)
+    vel = rng.standard_normal(system.pos.shape) * np.sqrt(boltzmann * 300.0 / system.masses)[:, None]
+    vel -= vel.mean(axis=0)
+    return system, vel
+
+
+def md_params(ensemble):
+    from micmec_b200.units import femtosecond, pascal
+
+    p = dict(timestep=10.0 * femtosecond, temp=300.0, press=1e6 * pascal, timecon_thermo=100.0 * femtosecond,
+             # 1e5 fs: the class default (1000 fs) is numerically unstable for these stiff cells at dt = 10 fs
+             # (the unmodified reference collapses the cell in two steps, see tests/golden/make_golden.py)
+             timecon_baro=1.0e5 * femtosecond, chain_vel0=np.array([1e-4, -2e-4, 5e-5]),
+             vel_press0=1e-8 * np.array([[1.0, 0.2, -0.1], [0.2, -0.5, 0.3], [-0.1, 0.3, 0.8]]))
+    p["thermo"] = ensemble in ("nvt", "npt")
+    p["baro"] = ensemble == "npt"
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (pynvml)."""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                self._stop_evt.wait(0.05)
+        except Exception as exc:  # pragma: no cover
+            self.reasons.add("unavailable: %s" % exc)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_oracle_rate(grid, ensemble, model, steps, nthreads):
+    """node-steps/s of the CPU oracle port (test infrastructure; here it is only the thing being TIMED as the
+    reported CPU baseline, never the product path)."""
+    from oracle import oracle as orc
+
+    system, vel = make_state(grid)
+    p = md_params(ensemble)
+    o = orc.Oracle(system, model=model, nthreads=nthreads)
+    thermo = dict(temp=p["temp"], timecon=p["timecon_thermo"], chain_vel0=p["chain_vel0"], chain_pos0=np.zeros(3)) if p["thermo"] else None
+    baro = dict(temp=p["temp"], press=p["press"], timecon=p["timecon_baro"], vel_press0=p["vel_press0"]) if p["baro"] else None
+    md = o.md(system.pos, vel, system.masses, np.array(system.domain.rvecs), p["timestep"], thermo=thermo, baro=baro)
+    md.run(1)
+    t0 = time.perf_counter()
+    md.run(steps)
+    dt = time.perf_counter() - t0
+    return system.nnodes * steps / dt, dt
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path = the pinned oracle port, all host threads."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    rate, dt = cpu_oracle_rate(args.cpu_grid, args.ensemble, args.model, args.steps, cores)
+    sample = "%d^3-cell fcu grid, %s, %d steps, OpenMP x%d (bounded sample of the %d^3 workload)" % (
+        args.cpu_grid, args.ensemble.upper(), args.steps, cores, args.grid)
+    line = {
+        "impl": "reference", "metric": "MD node-steps/s (force+Verlet, fp64)", "value": rate, "unit": "node-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": rate, "unit": "node-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "node-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {
+        "workload": "synthetic %dx%dx%d-cell fcu grid %s MD (%s), dt 10 fs" % (
+            args.grid, args.grid, args.grid, args.ensemble.upper(),
+            {"nve": "velocity Verlet", "nvt": "NHC thermostat", "npt": "NHC thermostat + MTK barostat"}[args.ensemble]),
+        "nodes_per_gpu": args.grid ** 3, "force_evals_per_step": FORCE_EVALS[args.ensemble], "model": args.model,
+        "parallelism": "single GPU" if world == 1 else "independent replicas x%d" % world,
+        "cache": "inputs larger than L2 (pos/vel/gpos %.0f MB each)" % (24.0 * args.grid ** 3 / 1e6),
+    }
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    from micmec_b200 import _lib
+    from micmec_b200.pes.mmff import MicMecForceField, ForcePartMechanical
+    from micmec_b200.sampling.verlet import VerletIntegrator
+    from micmec_b200.sampling.nvt import NHCThermostat
+    from micmec_b200.sampling.npt import MTKBarostat, TBCombination
+
+    lib = _lib.load()
+    system, vel0 = make_state(args.grid, seed=rank)
+    nnodes = system.nnodes
+    p = md_params(args.ensemble)
+    part = ForcePartMechanical(system, model=args.model, device=local_rank)
+    mmf = MicMecForceField(system, [part])
+    stream = torch.cuda.Stream(device=local_rank)
+    _lib.check(lib.mm_set_stream(part.handle, ctypes.c_void_p(stream.cuda_stream)))
+    hooks = []
+    thermo = baro = None
+    if p["thermo"]:
+        thermo = NHCThermostat(p["temp"], timecon=p["timecon_thermo"], chain_vel0=p["chain_vel0"], chain_pos0=np.zeros(3), restart=True)
+    if p["baro"]:
+        baro = MTKBarostat(mmf, p["temp"], p["press"], timecon=p["timecon_baro"], vel_press0=p["vel_press0"], restart=True)
+    if thermo is not None and baro is not None:
+        hooks.append(TBCombination(thermo, baro))
+    elif thermo is not None:
+        hooks.append(thermo)
+    verlet = VerletIntegrator(mmf, timestep=p["timestep"], hooks=hooks, vel0=vel0)
+    assert verlet.device_mode
+    md = verlet._md
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident value -------------------------------------------------------------------------------
+    _lib.check(lib.mm_md_run(md, max(args.warmup, 3)))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = part.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    _lib.check(lib.mm_md_run(md, args.steps))
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = part.launches - launches0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * nnodes * args.steps / (ms * 1e-3)
+    scal = np.zeros(_lib.S_COUNT)
+    _lib.check(lib.mm_md_scalars(md, _lib.ptr(scal)))  # raises on NaN: a diverged run is not a measurement
+
+    # ---- roofline of the dominant kernel (event-bracketed launches, separate short run) ----------------------------
+    _lib.check(lib.mm_set_option(part.handle, b"profile", 1))
+    nprof = max(3, min(args.steps, 10))
+    _lib.check(lib.mm_md_run(md, nprof))
+    nl, tot = ctypes.c_int64(), ctypes.c_double()
+    _lib.check(lib.mm_profile(part.handle, ctypes.byref(nl), ctypes.byref(tot)))
+    _lib.check(lib.mm_set_option(part.handle, b"profile", 0))
+    kernel_ms = tot.value / max(nl.value, 1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    fused = bool(getattr(part, "fused_step", False))
+    bytes_per_launch = (BYTES_PER_NODE_STEP if fused else BYTES_PER_NODE_EVAL) * nnodes
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "kernel": "fused force+Verlet step" if fused else "k_cells (per-cell force kernel)",
+        "bytes_per_node": BYTES_PER_NODE_STEP if fused else BYTES_PER_NODE_EVAL, "kernel_ms": kernel_ms,
+        "launches_timed": int(nl.value), "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
+        "step_frac_of_108B_roofline": (BYTES_PER_NODE_STEP * FORCE_EVALS[args.ensemble] * nnodes * args.steps / (ms * 1e-3) / 1e9) / peak,
+    }
+
+    # ---- e2e: host buffers in, one step, host buffers out, every step ---------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hpos = torch.empty((nnodes, 3), dtype=torch.float64).pin_memory()
+        hvel = torch.empty((nnodes, 3), dtype=torch.float64).pin_memory()
+        hp, hv = ctypes.c_void_p(hpos.data_ptr()), ctypes.c_void_p(hvel.data_ptr())
+        _lib.check(lib.mm_md_get_state(md, hp, hv, None, _lib.MM_HOST, None, None, None, None))
+        esteps = max(2, min(args.steps, 5))
+        sc = np.zeros(_lib.S_COUNT)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            _lib.check(lib.mm_md_set_state(md, hp, hv, _lib.MM_HOST))
+            _lib.check(lib.mm_md_run(md, 1))
+            _lib.check(lib.mm_md_get_state(md, hp, hv, None, _lib.MM_HOST, None, None, None, None))
+            _lib.check(lib.mm_md_scalars(md, _lib.ptr(sc)))
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * nnodes * esteps / dt, "unit": "node-steps/s", "h2d_bytes_per_step": 48 * nnodes,
+               "d2h_bytes_per_step": 48 * nnodes + 8 * _lib.S_COUNT, "steps": esteps,
+               "api": "mm_md_set_state(host) + mm_md_run(1) + mm_md_get_state(host) + mm_md_scalars per step"}
+
+    # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        csteps = 3
+        rate, dt = cpu_oracle_rate(args.cpu_grid, args.ensemble, args.model, csteps, cores)
+        cpu = {"value": rate, "unit": "node-steps/s", "cores": cores, "kind": "port",
+               "sample": "%d^3-cell fcu grid, %s, %d steps, OpenMP x%d, %.1f s" % (args.cpu_grid, args.ensemble.upper(), csteps, cores, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": "MD node-steps/s (force+Verlet, fp64)", "value": value, "unit": "node-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
+            "force_evals_per_s": value * FORCE_EVALS[args.ensemble],
+            "check": {"temp_K": scal[_lib.S_TEMP], "epot": scal[_lib.S_EPOT], "cons_err": scal[_lib.S_CONS_ERR]},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
