@@ -117,6 +117,7 @@ int mm_destroy(mm_handle *h) {
     cudaFree(h->d_partials);
     cudaFree(h->d_result);
     cudaFree(h->d_rvecs);
+    if (h->sg.active || h->sg.d_sc) sg_free(h);
     if (h->h_result) cudaFreeHost(h->h_result);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -283,6 +284,13 @@ int mm_create(const mm_desc *desc, mm_handle **out) {
     }
     MM_TRY(cudaStreamSynchronize(h->stream));
 #undef MM_TRY
+    if (sg_eligible(h) && h->nnodes >= 4096) {  // small grids are launch-bound either way: keep them on the simple path
+        const int rc = sg_setup(h);
+        if (rc != MM_OK) {
+            mm_destroy(h);
+            return rc;
+        }
+    }
     *out = h;
     return MM_OK;
 }
@@ -308,6 +316,19 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value) {
     if (!h || !name) return invalid("mm_set_option: null argument");
     if (strcmp(name, "scatter") == 0) {
         h->scatter_mode = value ? 1 : 0;
+        return MM_OK;
+    }
+    if (strcmp(name, "structured") == 0) {
+        // 1: use the structured-grid kernels (only full periodic grids with the `original` model qualify)
+        h->want_structured = value ? 1 : 0;
+        if (!value) {
+            h->sg.active = 0;
+            return MM_OK;
+        }
+        if (!sg_eligible(h)) return MM_OK;
+        MM_CUDA(cudaSetDevice(h->device));
+        if (!h->sg.d_sc) return sg_setup(h);
+        h->sg.active = 1;
         return MM_OK;
     }
     if (strcmp(name, "profile") == 0) {

@@ -137,7 +137,23 @@ int cells_launch(mm_handle *h) {
     return gc;
 }
 
+void final_launch(mm_handle *h, const double *pc, int nbc, const double *pn, int nbn) {
+    k_final<<<1, 256, 0, h->stream>>>(pc, nbc, pn, nbn, h->d_result);
+    h->launches++;
+}
+
 int force_evaluate(mm_handle *h, double *gpos_out, bool want_g2) {
+    if (h->sg.active) {  // structured-grid kernels: AoS -> SoA planes, marching force kernel, SoA -> AoS
+        int rc = sg_write_consts(h, h->rvecs, 0.0);
+        if (rc != MM_OK) return rc;
+        sg_pos_from_aos(h, h->d_pos);
+        rc = sg_force(h, gpos_out != nullptr);
+        if (rc != MM_OK) return rc;
+        if (gpos_out) sg_to_aos(h, 2, gpos_out);
+        final_launch(h, h->sg.d_partials, h->sg.nblocks, h->sg.d_partials + 13, gpos_out ? h->sg.nblocks : 0);
+        MM_CUDA(cudaGetLastError());
+        return MM_OK;
+    }
     double *pn = h->d_partials + (size_t)kMaxRedBlocks * kRedSlots;
     const int gc = cells_launch(h);
     int gn = 0;

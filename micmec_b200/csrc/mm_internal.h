@@ -9,6 +9,7 @@
 
 #include "../../include/micmec_b200.h"
 #include "mm_cell.cuh"
+#include "mm_structured.cuh"
 
 namespace mm {
 
@@ -66,6 +67,8 @@ struct mm_handle {
     int profile = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // one pair per timed force-kernel launch
     bool pos_valid = false;
+    int want_structured = 1;  // use the structured-grid kernels when the system allows it
+    mm::SGrid sg;
 };
 
 namespace mm {
@@ -81,5 +84,19 @@ int cells_launch(mm_handle *h);
 // event bracket around the dominant kernel when h->profile is on
 void prof_begin(mm_handle *h);
 void prof_end(mm_handle *h);
+void final_launch(mm_handle *h, const double *pc, int nbc, const double *pn, int nbn);
+
+// ---- mm_structured.cu ---------------------------------------------------------------------------------------
+bool sg_eligible(const mm_handle *h);
+int sg_setup(mm_handle *h);
+void sg_free(mm_handle *h);
+int sg_write_consts(mm_handle *h, const double *rvecs9, double dt);
+int sg_halo(mm_handle *h, bool pos, bool vel, bool grad);
+int sg_pos_from_aos(mm_handle *h, const double *d_aos);
+int sg_vel_from_aos(mm_handle *h, const double *d_aos);
+int sg_mass_from_aos(mm_handle *h, const double *d_masses);
+int sg_to_aos(mm_handle *h, int which, double *d_aos);
+int sg_force(mm_handle *h, bool write_g);
+int sg_step(mm_handle *h, bool write_g);
 
 }  // namespace mm

@@ -37,6 +37,8 @@ struct MDState {
     // pending transforms
     double Mvel[9];  // v_true = v_stored . Mvel
     double Rpos[9];  // to be applied by k_apply_pos
+    // structured path: positions stay in the frame of their last write; x_true = (x_stored + shifts(rv_stored)).Rpend
+    double Rpend[9], rv_stored[9];
     // Nose-Hoover chain
     int has_thermo, chain_len;
     double ch_temp, ch_timecon;
@@ -66,6 +68,7 @@ enum : unsigned {
     OP_ZERO_VIR = 1u << 9,
     OP_TAKE_DELTA = 1u << 10,
     OP_SETUP = 1u << 11,
+    OP_POS_WRITTEN = 1u << 12,
 };
 
 // ------------------------------------------------------------------------------------------- 3x3 helpers ----
@@ -208,6 +211,8 @@ __device__ void baro_a(MDState &s) {
     double nr[9];
     mat_mul(s.rvecs, s.Rpos, nr);
     for (int i = 0; i < 9; i++) s.rvecs[i] = nr[i];
+    mat_mul(s.Rpend, s.Rpos, nr);
+    for (int i = 0; i < 9; i++) s.Rpend[i] = nr[i];
 }
 
 // second half of MTKBarostat.baro (npt.py:708-736): velocity rotation (deferred), kinetic energy, barostat velocity
@@ -290,7 +295,7 @@ __device__ void properties(MDState &s, double n3) {  // verlet.py:171-190
 // One block.  Sums the block partials it is told to consume, then thread 0 runs the requested sub-steps in the
 // canonical order RESET_MVEL, TAKE_FORCE, TAKE_KIN, BARO_B, THERMO, BARO_A, ECONS, PROPS (see md_step below).
 __global__ void __launch_bounds__(256)
-k_scalar(MDState *st, double *rvecs_dev, unsigned ops, const double *pc, int nbc, const double *pn, int nbn,
+k_scalar(MDState *st, double *rvecs_dev, StepConsts *sc, unsigned ops, const double *pc, int nbc, const double *pn, int nbn,
          const double *pd, int nbd, double n3) {
     double fr[7] = {0, 0, 0, 0, 0, 0, 0}, kn[7] = {0, 0, 0, 0, 0, 0, 0}, dl[1] = {0};
     if (ops & OP_TAKE_FORCE) partials_sum<7>(pc, nbc, kRedSlots, fr);
@@ -300,6 +305,11 @@ k_scalar(MDState *st, double *rvecs_dev, unsigned ops, const double *pc, int nbc
     MDState &s = *st;
     if (ops & OP_RESET_MVEL)
         for (int i = 0; i < 9; i++) s.Mvel[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    if (ops & OP_POS_WRITTEN)  // the stored positions are the true ones again
+        for (int i = 0; i < 9; i++) {
+            s.Rpend[i] = (i % 4 == 0) ? 1.0 : 0.0;
+            s.rv_stored[i] = s.rvecs[i];
+        }
     if (ops & OP_TAKE_FORCE) {
         s.epot = fr[0];
         for (int k = 0; k < 6; k++) s.vir[k] = fr[1 + k];
@@ -342,6 +352,14 @@ k_scalar(MDState *st, double *rvecs_dev, unsigned ops, const double *pc, int nbc
         s.counter++;
     }
     if (ops & OP_PROPS) properties(s, n3);
+    if (sc) {
+        for (int i = 0; i < 9; i++) {
+            sc->Rpend[i] = s.Rpend[i];
+            sc->Mvel[i] = s.Mvel[i];
+            sc->rv[i] = s.rv_stored[i];
+        }
+        sc->dt = s.timestep;
+    }
 }
 
 // --------------------------------------------------------------------------------------- node kernels --------
@@ -449,7 +467,7 @@ k_moments(const double *__restrict__ vel, const double *__restrict__ masses, con
         acc[3] += m * vy * vz;
         acc[4] += m * vx * vz;
         acc[5] += m * vx * vy;
-        acc[6] += gpos[3 * i] * gpos[3 * i] + gpos[3 * i + 1] * gpos[3 * i + 1] + gpos[3 * i + 2] * gpos[3 * i + 2];
+        if (gpos) acc[6] += gpos[3 * i] * gpos[3 * i] + gpos[3 * i + 1] * gpos[3 * i + 1] + gpos[3 * i + 2] * gpos[3 * i + 2];
     }
     block_sum_store<7>(acc, partials + (size_t)blockIdx.x * kRedSlots);
 }
@@ -509,14 +527,19 @@ struct mm_md {
     double *d_pkin = nullptr;    // partials of node kernels [kMaxRedBlocks][kRedSlots]
     double *d_pdelta = nullptr;  // partials of k_delta
     bool initialised = false;
+    bool structured = false;  // state lives in the SoA planes of h->sg
 };
 
 namespace mm {
 
 static int scalar_launch(mm_md *md, unsigned ops, int nbc, int nbn, int nbd) {
     mm_handle *h = md->h;
-    k_scalar<<<1, 256, 0, h->stream>>>(md->d_state, h->d_rvecs, ops, h->d_partials, nbc, md->d_pkin, nbn, md->d_pdelta,
-                                       nbd, 3.0 * (double)h->nnodes);
+    const bool sg = md->structured;
+    // structured kernels leave all 14 sums of a block in one partial: energy + virial in slots 0-6, moments + g^2 in 7-13
+    const double *pc = sg ? h->sg.d_partials : h->d_partials;
+    const double *pn = sg ? h->sg.d_partials + 7 : md->d_pkin;
+    k_scalar<<<1, 256, 0, h->stream>>>(md->d_state, h->d_rvecs, sg ? h->sg.d_sc : nullptr, ops, pc, nbc, pn, nbn,
+                                       md->d_pdelta, nbd, 3.0 * (double)h->nnodes);
     h->launches++;
     return MM_OK;
 }
@@ -578,6 +601,82 @@ static int md_step(mm_md *md, bool full) {
             ops |= OP_TAKE_DELTA;
         }
         scalar_launch(md, ops, nbc, nbn, nbd);
+    }
+    return MM_OK;
+}
+
+// arr[n][3] <- arr[n][3] . M   with M (3x3) in device memory
+__global__ void __launch_bounds__(kNodeThreads)
+k_apply_mat9(const double *__restrict__ M9, double *__restrict__ arr, int64_t n) {
+    double M[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) M[i] = M9[i];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = arr[3 * i], y = arr[3 * i + 1], z = arr[3 * i + 2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) arr[3 * i + j] = x * M[j] + y * M[3 + j] + z * M[6 + j];
+    }
+}
+
+// true positions / velocities of the structured state as reference-ordered AoS arrays (h->d_pos, md->d_vel)
+static void sg_export(mm_md *md, bool pos, bool vel, double *pos_dst) {
+    mm_handle *h = md->h;
+    const int gn = grid_for(h, h->nnodes, kNodeThreads);
+    const double *sc = reinterpret_cast<const double *>(h->sg.d_sc);
+    if (pos) {
+        sg_to_aos(h, 0, pos_dst);
+        k_apply_mat9<<<gn, kNodeThreads, 0, h->stream>>>(sc, pos_dst, h->nnodes);  // StepConsts::Rpend
+        h->launches++;
+    }
+    if (vel) {
+        sg_to_aos(h, 1, md->d_vel);
+        k_apply_mat9<<<gn, kNodeThreads, 0, h->stream>>>(sc + 9, md->d_vel, h->nnodes);  // StepConsts::Mvel
+        h->launches++;
+    }
+}
+
+// The same step on the structured-grid kernels (mm_structured.cu): one fused kick-drift-force-kick launch, plus one
+// force-only launch per barostat call.  Pending rotations / scalings are consumed by the kernels on load.
+static int md_step_structured(mm_md *md, bool full) {
+    mm_handle *h = md->h;
+    const bool thermo = md->desc.has_thermo != 0, baro = md->desc.has_baro != 0;
+    const int nb = h->sg.nblocks;
+    if (full) sg_export(md, true, false, md->d_posold);  // posold of verlet.py:158-161
+    if (baro) {
+        scalar_launch(md, OP_BARO_A, 0, 0, 0);
+        sg_force(h, true);  // npt.py:702-707; its gradient is what the first kick uses
+        scalar_launch(md, OP_TAKE_FORCE | OP_BARO_B | (thermo ? OP_THERMO : 0u), nb, nb, 0);
+        sg_halo(h, false, false, true);
+    } else if (thermo) {
+        scalar_launch(md, OP_THERMO, 0, 0, 0);
+    }
+    // without a barostat the gradient written here feeds the next step's first kick
+    sg_step(h, !baro);
+    unsigned ops = OP_RESET_MVEL | OP_POS_WRITTEN | OP_TAKE_FORCE | OP_TAKE_KIN | (thermo ? OP_THERMO : 0u);
+    int nbd = 0;
+    if (!baro) {
+        sg_halo(h, true, true, true);  // rv_stored is unchanged without a barostat: safe before the scalar kernel
+        if (full) {
+            sg_export(md, true, false, h->d_pos);
+            nbd = grid_for(h, 3 * h->nnodes, kNodeThreads);
+            k_delta<<<nbd, kNodeThreads, 0, h->stream>>>(h->d_pos, md->d_posold, 3 * h->nnodes, md->d_pdelta);
+            h->launches++;
+            ops |= OP_TAKE_DELTA;
+        }
+        scalar_launch(md, ops | OP_ECONS | OP_ADVANCE | OP_PROPS, nb, nb, nbd);
+    } else {
+        scalar_launch(md, ops | OP_BARO_A, nb, nb, 0);
+        sg_halo(h, true, true, false);  // after OP_POS_WRITTEN: the halo shift must use the new stored frame
+        sg_force(h, full);
+        ops = OP_TAKE_FORCE | OP_BARO_B | OP_ECONS | OP_ADVANCE | OP_PROPS;
+        if (full) {
+            sg_export(md, true, false, h->d_pos);
+            nbd = grid_for(h, 3 * h->nnodes, kNodeThreads);
+            k_delta<<<nbd, kNodeThreads, 0, h->stream>>>(h->d_pos, md->d_posold, 3 * h->nnodes, md->d_pdelta);
+            h->launches++;
+            ops |= OP_TAKE_DELTA;
+        }
+        scalar_launch(md, ops, nb, nb, nbd);
     }
     return MM_OK;
 }
@@ -670,8 +769,10 @@ int mm_md_init(mm_md *md, const double *pos, const double *vel, const double *ma
     s.ndof = d.ndof;
     for (int i = 0; i < 9; i++) {
         s.rvecs[i] = rvecs9[i];
-        s.Mvel[i] = s.Rpos[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        s.Mvel[i] = s.Rpos[i] = s.Rpend[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        s.rv_stored[i] = rvecs9[i];
     }
+    md->structured = h->sg.active != 0;
     s.has_thermo = d.has_thermo;
     s.chain_len = d.has_thermo ? d.chain_length : 0;
     s.ch_temp = d.thermo_temp;
@@ -692,6 +793,29 @@ int mm_md_init(mm_md *md, const double *pos, const double *vel, const double *ma
     MM_CUDA(cudaMemcpyAsync(md->d_state, md->h_state, sizeof(MDState), cudaMemcpyHostToDevice, h->stream));
     // verlet.py:119-137: first force evaluation (no vtens unless a barostat re-evaluates, npt.py:612-614)
     const int gn = grid_for(h, nn, kNodeThreads);
+    if (md->structured) {
+        rc = sg_write_consts(h, rvecs9, d.timestep);
+        if (rc != MM_OK) return rc;
+        h->sg.cx = h->sg.cv = h->sg.cg = 0;
+        sg_pos_from_aos(h, h->d_pos);
+        sg_vel_from_aos(h, md->d_vel);
+        sg_mass_from_aos(h, md->d_masses);
+        sg_force(h, true);
+        sg_halo(h, false, false, true);
+        const int nb = h->sg.nblocks;
+        scalar_launch(md, OP_TAKE_FORCE | (d.has_baro ? 0u : OP_ZERO_VIR) | OP_SETUP, nb, nb, 0);
+        k_moments<<<gn, kNodeThreads, 0, h->stream>>>(md->d_vel, md->d_masses, nullptr, nn, md->d_pkin);
+        h->launches++;
+        // the moments come from the generic partial buffer this once: temporarily read them from there
+        md->structured = false;
+        scalar_launch(md, OP_TAKE_KIN | OP_PROPS, 0, gn, 0);
+        md->structured = true;
+        scalar_launch(md, 0u, 0, 0, 0);  // publish the StepConsts (dt, frames) for the structured kernels
+        MM_CUDA(cudaGetLastError());
+        MM_CUDA(cudaStreamSynchronize(h->stream));
+        md->initialised = true;
+        return MM_OK;
+    }
     const int nbc = cells_launch(h);
     k_gather_g2<<<gn, kNodeThreads, 0, h->stream>>>(h->d_node_cells, h->d_gcell, nn, h->ncells, h->d_gpos, md->d_pkin);
     h->launches++;
@@ -721,6 +845,13 @@ int mm_md_set_state(mm_md *md, const double *pos, const double *vel, int where) 
         scalar_launch(md, OP_RESET_MVEL, 0, 0, 0);
         MM_CUDA(cudaMemcpyAsync(md->d_vel, vel, sizeof(double) * 3 * h->nnodes, kind, h->stream));
     }
+    if (md->structured) {
+        if (pos) {
+            scalar_launch(md, OP_POS_WRITTEN, 0, 0, 0);  // uploaded positions are in the true frame
+            sg_pos_from_aos(h, h->d_pos);
+        }
+        if (vel) sg_vel_from_aos(h, md->d_vel);
+    }
     return MM_OK;
 }
 
@@ -730,7 +861,10 @@ int mm_md_run(mm_md *md, int64_t nsteps) {
         return MM_ERR_STATE;
     }
     MM_CUDA(cudaSetDevice(md->h->device));
-    for (int64_t i = 0; i < nsteps; i++) md_step(md, i == nsteps - 1);
+    for (int64_t i = 0; i < nsteps; i++) {
+        if (md->structured) md_step_structured(md, i == nsteps - 1);
+        else md_step(md, i == nsteps - 1);
+    }
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
@@ -745,7 +879,12 @@ int mm_md_get_state(mm_md *md, double *pos, double *vel, double *gpos, int where
     const int64_t nn = h->nnodes;
     MM_CUDA(cudaSetDevice(h->device));
     const cudaMemcpyKind kind = where == MM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    if (vel) {
+    if (md->structured) {
+        // export copies of the SoA state in reference order; the device state (and its pending transforms) is untouched
+        sg_export(md, pos != nullptr, vel != nullptr, h->d_pos);
+        if (gpos) sg_to_aos(h, 2, h->d_gpos);
+        if (vel) MM_CUDA(cudaMemcpyAsync(vel, md->d_vel, sizeof(double) * 3 * nn, kind, h->stream));
+    } else if (vel) {
         const int gn = grid_for(h, nn, kNodeThreads);
         k_flush_vel<<<gn, kNodeThreads, 0, h->stream>>>(md->d_state, md->d_vel, nn);
         h->launches++;

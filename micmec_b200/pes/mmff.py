@@ -109,9 +109,13 @@ class ForcePartMechanical(ForcePart):
         matrices).  Defaults to ``$MICMEC_MODEL`` or ``"original"``.
     device : int, optional
         CUDA device ordinal.
+    structured : bool, optional
+        Full periodic grids built without index arrays (``System.periodic_grid``) can run on the structured-grid
+        kernels (fused force + Verlet, no per-cell data in HBM).  ``None`` lets the library decide (grids of at
+        least 4096 nodes), ``True`` / ``False`` force the choice; systems that do not qualify ignore it.
     """
 
-    def __init__(self, system, model=None, device=0):
+    def __init__(self, system, model=None, device=0, structured=None):
         ForcePart.__init__(self, "micmec", system)
         self.system = system
         self.model = model or os.environ.get("MICMEC_MODEL", "original")
@@ -122,7 +126,8 @@ class ForcePartMechanical(ForcePart):
         self._lib = _lib.load()
         self._handle = ctypes.c_void_p()
         self._keep = self._create()
-        self.nlaunch0 = 0
+        if structured is not None:
+            _lib.check(self._lib.mm_set_option(self._handle, b"structured", int(bool(structured))))
 
     @staticmethod
     def get_pbc(rvecs):

@@ -210,3 +210,61 @@ def test_errors_match_reference():
     system = System.periodic_grid((3, 3, 3), TYPE_TEST)
     with pytest.raises(ValueError):
         ForcePartMechanical(system, model="nonsense")
+
+
+def two_type_params():
+    """Two cell types; type 2 has two metastable states close enough in energy to mix."""
+    from micmec_b200.celltypes import TYPE_FCU, TYPE_TEST
+
+    params = {}
+    for key in ("cell", "elasticity", "free_energy", "effective_temp", "mass"):
+        params["type1/" + key] = TYPE_FCU[key]
+    h0 = TYPE_FCU["cell"][0]
+    params["type2/cell"] = np.array([h0 * 1.01, h0 * 1.03])
+    params["type2/elasticity"] = np.array([TYPE_FCU["elasticity"][0] * 0.8, TYPE_FCU["elasticity"][0] * 0.6])
+    params["type2/free_energy"] = np.array([0.0, 3.0e-4])
+    params["type2/effective_temp"] = 350.0
+    params["type2/mass"] = TYPE_FCU["mass"]
+    return params
+
+
+@pytest.mark.parametrize("shape,mixed", [((12, 10, 8), False), ((33, 7, 5), False), ((40, 20, 70), False),
+                                         ((16, 12, 10), True), ((2, 2, 3), True)])
+def test_structured_kernels_match_generic_and_oracle(shape, mixed):
+    """The marching structured-grid kernel (mm_structured.cu) vs the indexed kernels vs the oracle."""
+    from micmec_b200.system import System
+    from micmec_b200.celltypes import TYPE_FCU
+
+    system = System.periodic_grid(shape, TYPE_FCU, explicit=True)
+    rng = np.random.default_rng(3)
+    if mixed:
+        system.types = rng.integers(1, 3, size=system.ncells)
+        system.grid = system.types.reshape(shape)
+        system.params = two_type_params()
+    pos = system.pos + 0.4 * rng.standard_normal(system.pos.shape)
+    strain = np.eye(3) + 0.01 * rng.standard_normal((3, 3))
+    pos, rvecs = pos @ strain, np.ascontiguousarray(system.domain.rvecs @ strain)
+    res = {}
+    for structured in (False, True):
+        sysx = System(system.pos.copy(), system.masses, np.array(system.domain.rvecs), None if structured else system.surrounding_cells,
+                      None if structured else system.surrounding_nodes, grid=system.grid, types=system.types,
+                      params=system.params, structured_shape=shape)
+        from micmec_b200.pes.mmff import MicMecForceField, ForcePartMechanical
+
+        part = ForcePartMechanical(sysx, model="original", structured=structured)
+        mmf = MicMecForceField(sysx, [part])
+        mmf.update_rvecs(rvecs)
+        mmf.update_pos(pos)
+        g, v = np.zeros(pos.shape), np.zeros((3, 3))
+        res[structured] = (mmf.compute(g, v), g, v)
+        v2 = np.zeros((3, 3))
+        assert mmf.compute(vtens=v2) == res[structured][0] and np.array_equal(v2, v)  # vtens without gpos
+    ea, ga, va = res[False]
+    eb, gb, vb = res[True]
+    assert abs(ea - eb) <= 1e-12 * abs(ea)
+    assert gio.rel_rms(gb, ga) <= 1e-11
+    assert gio.rel_rms(vb, va) <= 1e-11
+    oracle = orc.Oracle(system, model="original", nthreads=8)
+    eo, go, vo = oracle.compute(pos, rvecs, gpos=True, vtens=True)
+    _, gc, vc = oracle.deformation(pos, rvecs)
+    check_against(eb, gb, vb, eo, go, vo, gio.virial_noise(gc, vc))

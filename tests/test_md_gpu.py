@@ -83,8 +83,10 @@ def test_trajectory_matches_reference_golden(name):
             assert gio.rel_rms(np.asarray(baro.vel_press), d[p + "vel_press"]) <= max(xtol, 1e-9)
 
 
-def test_matches_oracle_md_on_larger_grid():
-    """NVT + NPT on a perturbed 6x5x4 fcu grid: CUDA integrator vs the CPU oracle's MD, 40 steps."""
+@pytest.mark.parametrize("structured", [False, True])
+def test_matches_oracle_md_on_larger_grid(structured):
+    """NVE + NVT + NPT on a perturbed 6x5x4 fcu grid: CUDA integrator (indexed kernels / structured-grid fused
+    kernels) vs the CPU oracle's MD, 40 steps."""
     from oracle import oracle as orc
     from micmec_b200.system import System
     from micmec_b200.celltypes import TYPE_FCU
@@ -95,16 +97,20 @@ def test_matches_oracle_md_on_larger_grid():
     from micmec_b200.units import femtosecond, pascal
 
     rng = np.random.default_rng(8)
-    for ens in ("nvt", "npt"):
+    for ens in ("nve", "nvt", "npt"):
         system = System.periodic_grid((6, 5, 4), TYPE_FCU, explicit=True)
         system.pos[:] = system.pos + 0.2 * rng.standard_normal(system.pos.shape)
-        mmf = MicMecForceField(system, [ForcePartMechanical(system)])
+        sysx = system
+        if structured:
+            sysx = System.periodic_grid((6, 5, 4), TYPE_FCU, explicit=False)
+            sysx.pos[:] = system.pos
+        mmf = MicMecForceField(sysx, [ForcePartMechanical(sysx, structured=structured)])
         vel0 = 1e-5 * rng.standard_normal(system.pos.shape)
         vel0 -= vel0.mean(axis=0)
         cvel = np.array([1e-4, -2e-4, 5e-5])
         vp0 = 1e-6 * np.array([[1.0, 0.2, -0.1], [0.2, -0.5, 0.3], [-0.1, 0.3, 0.8]])
         thermo = NHCThermostat(300.0, timecon=100 * femtosecond, chain_vel0=cvel, chain_pos0=np.zeros(3), restart=True)
-        hooks = [thermo]
+        hooks = [thermo] if ens != "nve" else []
         baro_kw = None
         if ens == "npt":
             baro = MTKBarostat(mmf, 300.0, 1e6 * pascal, timecon=1e5 * femtosecond, vel_press0=vp0, restart=True)
@@ -113,7 +119,8 @@ def test_matches_oracle_md_on_larger_grid():
         verlet = VerletIntegrator(mmf, timestep=10 * femtosecond, hooks=hooks, vel0=vel0)
         o = orc.Oracle(system, nthreads=2)
         md = o.md(system.pos, vel0, system.masses, np.array(system.domain.rvecs), 10 * femtosecond,
-                  thermo=dict(temp=300.0, timecon=100 * femtosecond, chain_vel0=cvel, chain_pos0=np.zeros(3)), baro=baro_kw)
+                  thermo=dict(temp=300.0, timecon=100 * femtosecond, chain_vel0=cvel, chain_pos0=np.zeros(3))
+                  if ens != "nve" else None, baro=baro_kw)
         for _ in range(4):
             verlet.run(10)
             md.run(10)
@@ -121,7 +128,12 @@ def test_matches_oracle_md_on_larger_grid():
             assert gio.rel_rms(verlet.vel, md.vel) <= 1e-8
             assert abs(verlet.econs - md.econs) <= 1e-8 * abs(md.econs)
             assert abs(verlet.temp - md.temp) <= 1e-8 * md.temp
-            assert gio.rel_rms(thermo.chain.vel, md.chain_vel) <= 1e-7
+            assert gio.rel_rms(verlet.gpos, md.gpos) <= 1e-8
+            assert abs(verlet.rmsd_delta - md.rmsd_delta) <= 1e-8 * md.rmsd_delta
+            assert abs(verlet.rmsd_gpos - md.rmsd_gpos) <= 1e-8 * md.rmsd_gpos
+            assert abs(verlet.press - md.press) <= 1e-7 * abs(md.press)
+            if ens != "nve":
+                assert gio.rel_rms(thermo.chain.vel, md.chain_vel) <= 1e-7
 
 
 class CountingHook(object):
