@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--cpu-grid", type=int, default=48, help="edge of the bounded CPU sample grid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tile-rows", type=int, default=0, help="tuning: warps per block of the marching kernel (8/12/16)")
+    ap.add_argument("--ahg", type=int, default=-1, help="tuning: elasticity block via global loads (0/1)")
+    ap.add_argument("--generic", action="store_true", help="force the indexed-topology kernels (no structured path)")
     return ap.parse_args()
 
 
@@ -193,7 +196,11 @@ def main():
     system, vel0 = make_state(args.grid, seed=rank)
     nnodes = system.nnodes
     p = md_params(args.ensemble)
-    part = ForcePartMechanical(system, model=args.model, device=local_rank)
+    part = ForcePartMechanical(system, model=args.model, device=local_rank, structured=False if args.generic else None)
+    if args.tile_rows:
+        _lib.check(lib.mm_set_option(part.handle, b"tile_rows", args.tile_rows))
+    if args.ahg >= 0:
+        _lib.check(lib.mm_set_option(part.handle, b"ahg", args.ahg))
     mmf = MicMecForceField(system, [part])
     stream = torch.cuda.Stream(device=local_rank)
     _lib.check(lib.mm_set_stream(part.handle, ctypes.c_void_p(stream.cuda_stream)))

@@ -331,6 +331,17 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value) {
         h->sg.active = 1;
         return MM_OK;
     }
+    if (strcmp(name, "ahg") == 0) {
+        h->sg.ahg = value ? 1 : 0;
+        return MM_OK;
+    }
+    if (strcmp(name, "tile_rows") == 0) {
+        if (!h->sg.d_sc) return MM_OK;
+        MM_CUDA(cudaSetDevice(h->device));
+        MM_CUDA(cudaStreamSynchronize(h->stream));
+        if (sg_set_tile_rows(h, (int)value) != MM_OK) return invalid("mm_set_option: tile_rows must be 8");
+        return MM_OK;
+    }
     if (strcmp(name, "profile") == 0) {
         h->profile = value ? 1 : 0;
         return MM_OK;

@@ -147,7 +147,7 @@ int force_evaluate(mm_handle *h, double *gpos_out, bool want_g2) {
         int rc = sg_write_consts(h, h->rvecs, 0.0);
         if (rc != MM_OK) return rc;
         sg_pos_from_aos(h, h->d_pos);
-        rc = sg_force(h, gpos_out != nullptr);
+        rc = sg_force(h, gpos_out != nullptr, 0);
         if (rc != MM_OK) return rc;
         if (gpos_out) sg_to_aos(h, 2, gpos_out);
         final_launch(h, h->sg.d_partials, h->sg.nblocks, h->sg.d_partials + 13, gpos_out ? h->sg.nblocks : 0);

@@ -96,7 +96,8 @@ int sg_pos_from_aos(mm_handle *h, const double *d_aos);
 int sg_vel_from_aos(mm_handle *h, const double *d_aos);
 int sg_mass_from_aos(mm_handle *h, const double *d_masses);
 int sg_to_aos(mm_handle *h, int which, double *d_aos);
-int sg_force(mm_handle *h, bool write_g);
-int sg_step(mm_handle *h, bool write_g);
+int sg_force(mm_handle *h, bool write_g, int rot);
+int sg_step(mm_handle *h, bool write_g, int vm, bool lean);
+int sg_set_tile_rows(mm_handle *h, int rows);
 
 }  // namespace mm

@@ -644,14 +644,16 @@ static int md_step_structured(mm_md *md, bool full) {
     if (full) sg_export(md, true, false, md->d_posold);  // posold of verlet.py:158-161
     if (baro) {
         scalar_launch(md, OP_BARO_A, 0, 0, 0);
-        sg_force(h, true);  // npt.py:702-707; its gradient is what the first kick uses
-        scalar_launch(md, OP_TAKE_FORCE | OP_BARO_B | (thermo ? OP_THERMO : 0u), nb, nb, 0);
-        sg_halo(h, false, false, true);
+        // npt.py:683-707: rotate the positions (all pending rotations at once) and evaluate; the rotated positions are
+        // written back so that the fused step below needs no rotation; the gradient is what its first kick uses
+        sg_force(h, true, 2);
+        scalar_launch(md, OP_POS_WRITTEN | OP_TAKE_FORCE | OP_BARO_B | (thermo ? OP_THERMO : 0u), nb, nb, 0);
+        sg_halo(h, true, false, true);  // after OP_POS_WRITTEN: the halo shift uses the new stored frame
     } else if (thermo) {
         scalar_launch(md, OP_THERMO, 0, 0, 0);
     }
     // without a barostat the gradient written here feeds the next step's first kick
-    sg_step(h, !baro);
+    sg_step(h, !baro, baro ? 2 : (thermo ? 1 : 0), !full);
     unsigned ops = OP_RESET_MVEL | OP_POS_WRITTEN | OP_TAKE_FORCE | OP_TAKE_KIN | (thermo ? OP_THERMO : 0u);
     int nbd = 0;
     if (!baro) {
@@ -667,7 +669,7 @@ static int md_step_structured(mm_md *md, bool full) {
     } else {
         scalar_launch(md, ops | OP_BARO_A, nb, nb, 0);
         sg_halo(h, true, true, false);  // after OP_POS_WRITTEN: the halo shift must use the new stored frame
-        sg_force(h, full);
+        sg_force(h, full, 1);           // npt.py:683-707 again; this rotation stays pending until the next step
         ops = OP_TAKE_FORCE | OP_BARO_B | OP_ECONS | OP_ADVANCE | OP_PROPS;
         if (full) {
             sg_export(md, true, false, h->d_pos);
@@ -800,7 +802,7 @@ int mm_md_init(mm_md *md, const double *pos, const double *vel, const double *ma
         sg_pos_from_aos(h, h->d_pos);
         sg_vel_from_aos(h, md->d_vel);
         sg_mass_from_aos(h, md->d_masses);
-        sg_force(h, true);
+        sg_force(h, true, 0);
         sg_halo(h, false, false, true);
         const int nb = h->sg.nblocks;
         scalar_launch(md, OP_TAKE_FORCE | (d.has_baro ? 0u : OP_ZERO_VIR) | OP_SETUP, nb, nb, 0);

@@ -18,319 +18,16 @@
 //    scalings (StepConsts) are applied on load, so there is no separate "scale velocities" / "rotate positions" pass;
 //  * energy, virial (6) and the kinetic second moments (6) are reduced with warp shuffles into one partial per block.
 //
-// Apron cells are recomputed by neighbouring blocks (tile 32 x 8 threads -> 30 x 6 owned nodes): the price of never
-// materialising per-cell data.  DESIGN.md discusses the trade-off and the measured numbers.
+// Apron cells are recomputed by neighbouring blocks (tile 32 x TY threads -> 30 x (TY-2) owned nodes): the price of
+// never materialising per-cell data.  DESIGN.md discusses the trade-off and the measured numbers.  The kernel itself
+// lives in mm_march.cuh; this file holds the layout conversions, halo planes and the launch logic.
 #include <vector>
 
 #include "mm_internal.h"
+#include "mm_march.cuh"
 #include "mm_reduce.cuh"
 
 namespace mm {
-
-constexpr int TX = 32, TY = 8;
-constexpr int OX = TX - 2, OY = TY - 2;
-
-// ---------------------------------------------------------------------------------------------------------------
-// one state of one cell from Hs = 4 H (rows = summed edge vectors)
-__device__ __forceinline__ void sstate_eval(const double Hs[9], const SState &P, double &e, double D[9], double vir[6]) {
-    double G[9];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-            G[i * 3 + j] = fma(P.hiq[i * 3 + 2], Hs[6 + j], fma(P.hiq[i * 3 + 1], Hs[3 + j], P.hiq[i * 3] * Hs[j]));
-    double u[6];  // u = G G^T - I = 2 eps
-    u[0] = fma(G[2], G[2], fma(G[1], G[1], fma(G[0], G[0], -1.0)));
-    u[1] = fma(G[5], G[5], fma(G[4], G[4], fma(G[3], G[3], -1.0)));
-    u[2] = fma(G[8], G[8], fma(G[7], G[7], fma(G[6], G[6], -1.0)));
-    u[3] = fma(G[5], G[8], fma(G[4], G[7], G[3] * G[6]));
-    u[4] = fma(G[2], G[8], fma(G[1], G[7], G[0] * G[6]));
-    u[5] = fma(G[2], G[5], fma(G[1], G[4], G[0] * G[3]));
-    double s[6];
-#pragma unroll
-    for (int I = 0; I < 6; I++) {
-        double acc = P.Ah[I * 6] * u[0];
-#pragma unroll
-        for (int J = 1; J < 6; J++) acc = fma(P.Ah[I * 6 + J], u[J], acc);
-        s[I] = acc;
-    }
-    const double dens = fma(2.0, fma(u[5], s[5], fma(u[4], s[4], u[3] * s[3])), fma(u[2], s[2], fma(u[1], s[1], u[0] * s[0])));
-    e = P.v0q * dens;
-    double T[9];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        T[j] = fma(s[4], G[6 + j], fma(s[5], G[3 + j], s[0] * G[j]));
-        T[3 + j] = fma(s[3], G[6 + j], fma(s[1], G[3 + j], s[5] * G[j]));
-        T[6 + j] = fma(s[2], G[6 + j], fma(s[3], G[3 + j], s[4] * G[j]));
-    }
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-            D[i * 3 + j] = fma(P.hitv[i * 3 + 2], T[6 + j], fma(P.hitv[i * 3 + 1], T[3 + j], P.hitv[i * 3] * T[j]));
-    vir[0] = P.v0 * fma(G[6], T[6], fma(G[3], T[3], G[0] * T[0]));
-    vir[1] = P.v0 * fma(G[7], T[7], fma(G[4], T[4], G[1] * T[1]));
-    vir[2] = P.v0 * fma(G[8], T[8], fma(G[5], T[5], G[2] * T[2]));
-    vir[3] = P.v0 * fma(G[7], T[8], fma(G[4], T[5], G[1] * T[2]));
-    vir[4] = P.v0 * fma(G[6], T[8], fma(G[3], T[5], G[0] * T[2]));
-    vir[5] = P.v0 * fma(G[6], T[7], fma(G[3], T[4], G[0] * T[1]));
-}
-
-// all states of a cell, Boltzmann-mixed (mmff.py:377-398); the mixing is linear in the gradient, hence in D
-template <bool SINGLE>
-__device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp, int type, double &e, double D[9], double vir[6]) {
-    if (SINGLE) {
-        sstate_eval(Hs, kp.st[0], e, D, vir);
-        e += kp.st[0].efree;
-        return;
-    }
-    const int ns = kp.nstates[type], off = kp.offset[type];
-    sstate_eval(Hs, kp.st[off], e, D, vir);
-    e += kp.st[off].efree;
-    if (ns == 1) return;
-    const double kT = kp.kT[type];
-    double emin = e, wsum = 1.0;
-#pragma unroll 1
-    for (int s = 1; s < ns; s++) {
-        double es, Ds[9], vs[6];
-        sstate_eval(Hs, kp.st[off + s], es, Ds, vs);
-        es += kp.st[off + s].efree;
-        double fo, fn;  // factors for the old accumulation and the new state
-        if (es < emin) {
-            fo = exp(-(emin - es) / kT);
-            fn = 1.0;
-            emin = es;
-        } else {
-            fo = 1.0;
-            fn = exp(-(es - emin) / kT);
-        }
-        wsum = fma(wsum, fo, fn);
-#pragma unroll
-        for (int k = 0; k < 9; k++) D[k] = fma(D[k], fo, fn * Ds[k]);
-#pragma unroll
-        for (int k = 0; k < 6; k++) vir[k] = fma(vir[k], fo, fn * vs[k]);
-    }
-    const double inv = 1.0 / wsum;
-#pragma unroll
-    for (int k = 0; k < 9; k++) D[k] *= inv;
-#pragma unroll
-    for (int k = 0; k < 6; k++) vir[k] *= inv;
-    e = emin - kT * log(wsum);
-}
-
-__device__ __forceinline__ double shfl_down1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
-__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
-
-// ---------------------------------------------------------------------------------------------------------------
-template <bool STEP, bool WRITE_G, bool SINGLE>
-__global__ void __launch_bounds__(TX *TY)
-k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a) {
-    __shared__ double sf[6][TY][TX];  // forward exchange along y: (px, dx) of the row above
-    __shared__ double sb[9][TY][TX];  // backward exchange along y: z-combined D rows of the row below
-
-    const int lane = threadIdx.x, row = threadIdx.y;
-    const int nx = a.nx, ny = a.ny;
-    const int k = blockIdx.x * OX + lane - 1, l = blockIdx.y * OY + row - 1;
-    // periodic images along x and y (floor division handles grids narrower than a tile)
-    const int qx = (k >= 0) ? k / nx : -((-k + nx - 1) / nx);
-    const int qy = (l >= 0) ? l / ny : -((-l + ny - 1) / ny);
-    const int kk = k - qx * nx, ll = l - qy * ny;
-    const bool own_xy = lane >= 1 && lane <= OX && row >= 1 && row <= OY && k < nx && l < ny;
-    const StepConsts &sc = *a.sc;
-    const double shx = qx * sc.rv[0] + qy * sc.rv[3];
-    const double shy = qx * sc.rv[1] + qy * sc.rv[4];
-    const double shz = qx * sc.rv[2] + qy * sc.rv[5];
-    double R[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) R[i] = sc.Rpend[i];
-    const double dt = sc.dt, hdt = 0.5 * sc.dt;
-
-    const int64_t plane = (int64_t)nx * ny;
-    const int c0 = 1 + blockIdx.z * a.chunk;
-    const int c1 = min(c0 + a.chunk, a.nzl + 1);
-    int64_t idx = ((int64_t)(c0 - 1) * ny + ll) * nx + kk;  // node (kk, ll) in array plane p
-
-    double acc[14];
-#pragma unroll
-    for (int i = 0; i < 14; i++) acc[i] = 0.0;
-
-    // carried from plane to plane
-    double fpxy[3], fdxy[3], fpyd[3];   // forward: xy-combined sums / differences of the previous plane
-    double Dp[9];                       // D' of the previous cell layer
-    double vh[3] = {0, 0, 0}, mprev = 0.0, hminv_prev = 0.0;  // STEP: half-kicked velocity / mass of the previous plane
-
-    // software pipeline: raw loads of the NEXT plane are issued before the arithmetic of the current one
-    double nx_[3], nv_[3], ng_[3], nm_ = 0.0, nminv_ = 0.0;
-    auto issue_loads = [&](int64_t at) {
-#pragma unroll
-        for (int d = 0; d < 3; d++) nx_[d] = a.x[d][at];
-        if (STEP) {
-#pragma unroll
-            for (int d = 0; d < 3; d++) {
-                nv_[d] = a.v[d][at];
-                ng_[d] = a.g[d][at];
-            }
-            nm_ = a.m[at];
-            nminv_ = a.minv[at];
-        }
-    };
-    issue_loads(idx);
-
-    for (int p = c0 - 1; p <= c1; p++, idx += plane) {
-        double cx[3] = {nx_[0], nx_[1], nx_[2]};
-        double cv[3], cg[3], cm = nm_, cminv = nminv_;
-        if (STEP) {
-#pragma unroll
-            for (int d = 0; d < 3; d++) {
-                cv[d] = nv_[d];
-                cg[d] = ng_[d];
-            }
-        }
-        if (p < c1) issue_loads(idx + plane);
-
-        // ---- node (lane, row, p): true position (and, in STEP mode, kick + drift: verlet.py:144-146) -------------
-        const double xs = cx[0] + shx, ys = cx[1] + shy, zs = cx[2] + shz;
-        double r[3];
-#pragma unroll
-        for (int j = 0; j < 3; j++) r[j] = fma(zs, R[6 + j], fma(ys, R[3 + j], xs * R[j]));
-        double vcur[3] = {0, 0, 0};
-        const double hminv = hdt * cminv;
-        if (STEP) {
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const double vt = fma(cv[2], sc.Mvel[6 + j], fma(cv[1], sc.Mvel[3 + j], cv[0] * sc.Mvel[j]));
-                vcur[j] = fma(-hminv, cg[j], vt);
-                r[j] = fma(dt, vcur[j], r[j]);
-            }
-            if (own_xy && p >= c0 && p < c1) {
-#pragma unroll
-                for (int j = 0; j < 3; j++) a.xo[j][idx] = r[j];
-            }
-        }
-
-        // ---- forward butterfly: x by shuffle, y through shared memory, z in registers ------------------------------
-        double px[3], dx[3];
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const double rn = shfl_down1(r[j]);
-            px[j] = rn + r[j];
-            dx[j] = rn - r[j];
-            sf[j][row][lane] = px[j];
-            sf[3 + j][row][lane] = dx[j];
-        }
-        __syncthreads();
-        const int rowp = (row + 1 < TY) ? row + 1 : row;
-        double pxy[3], dxy[3], pyd[3];
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const double pxn = sf[j][rowp][lane], dxn = sf[3 + j][rowp][lane];
-            pxy[j] = px[j] + pxn;
-            dxy[j] = dx[j] + dxn;
-            pyd[j] = pxn - px[j];
-        }
-
-        double g[3] = {0, 0, 0};
-        const bool have_cell = p >= c0;       // cell layer p-1 (planes p-1 and p)
-        const bool have_node = p >= c0 + 1;   // node plane p-1 (cell layers p-2 and p-1)
-        double D[9];
-        if (have_cell) {
-            double Hs[9];
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                Hs[j] = fdxy[j] + dxy[j];        // 4 * (mean x edge)
-                Hs[3 + j] = fpyd[j] + pyd[j];    // 4 * (mean y edge)
-                Hs[6 + j] = pxy[j] - fpxy[j];    // 4 * (mean z edge)
-            }
-            const int type = SINGLE ? 0 : (int)a.type[idx - plane];
-            double e, vir[6];
-            scell_eval<SINGLE>(Hs, kp, type, e, D, vir);
-            if (own_xy && have_node) {  // the warm-up layer c0-1 belongs to the chunk below
-                acc[0] += e;
-#pragma unroll
-                for (int q = 0; q < 6; q++) acc[1 + q] += vir[q];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            fpxy[j] = pxy[j];
-            fdxy[j] = dxy[j];
-            fpyd[j] = pyd[j];
-        }
-
-        // ---- backward butterfly: z in registers, y through shared memory, x by shuffle ---------------------------
-        if (have_node) {
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                sb[j][row][lane] = Dp[j] + D[j];
-                sb[3 + j][row][lane] = Dp[3 + j] + D[3 + j];
-                sb[6 + j][row][lane] = Dp[6 + j] - D[6 + j];
-            }
-        }
-        __syncthreads();
-        if (have_node) {
-            const int rowm = (row > 0) ? row - 1 : row;
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const double q0 = sb[j][rowm][lane] + sb[j][row][lane];
-                const double q1 = sb[3 + j][rowm][lane] - sb[3 + j][row][lane];
-                const double q2 = sb[6 + j][rowm][lane] + sb[6 + j][row][lane];
-                const double s12 = q1 + q2;
-                const double q0m = shfl_up1(q0), s12m = shfl_up1(s12);
-                g[j] = (q0m - q0) + (s12m + s12);
-            }
-            if (own_xy) {
-                const int64_t at = idx - plane;
-                if (STEP) {  // second kick (verlet.py:152-153) + kinetic moments of the new velocities
-                    double vn[3];
-#pragma unroll
-                    for (int j = 0; j < 3; j++) {
-                        vn[j] = fma(-hminv_prev, g[j], vh[j]);
-                        a.vo[j][at] = vn[j];
-                    }
-                    acc[7] = fma(mprev * vn[0], vn[0], acc[7]);
-                    acc[8] = fma(mprev * vn[1], vn[1], acc[8]);
-                    acc[9] = fma(mprev * vn[2], vn[2], acc[9]);
-                    acc[10] = fma(mprev * vn[1], vn[2], acc[10]);
-                    acc[11] = fma(mprev * vn[0], vn[2], acc[11]);
-                    acc[12] = fma(mprev * vn[0], vn[1], acc[12]);
-                }
-                if (WRITE_G) {
-#pragma unroll
-                    for (int j = 0; j < 3; j++) a.go[j][at] = g[j];
-                }
-                acc[13] += fma(g[0], g[0], fma(g[1], g[1], g[2] * g[2]));
-            }
-        }
-        if (have_cell) {
-#pragma unroll
-            for (int q = 0; q < 9; q++) Dp[q] = D[q];
-        }
-        if (STEP) {
-#pragma unroll
-            for (int j = 0; j < 3; j++) vh[j] = vcur[j];
-            mprev = cm;
-            hminv_prev = hminv;
-        }
-    }
-    const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    // block_sum_store expects a 1-D thread index
-    {
-        __shared__ double red[TY][14];
-        const int warp = row;
-#pragma unroll
-        for (int q = 0; q < 14; q++) {
-            const double s = warp_sum(acc[q]);
-            if (lane == 0) red[warp][q] = s;
-        }
-        __syncthreads();
-        if (warp == 0 && lane < 14) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < TY; w++) s += red[w][lane];
-            a.partials[(size_t)bid * kRedSlots + lane] = s;
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // halo planes: p = 0 <- p = nzl (minus c), p = nzl + 1 <- p = 1 (plus c); c = third domain vector of the stored frame
@@ -434,7 +131,8 @@ bool sg_eligible(const mm_handle *h) {
 
 int sg_blocks(const mm_handle *h, dim3 &grid) {
     const SGrid &g = h->sg;
-    grid = dim3((g.nx + OX - 1) / OX, (g.ny + OY - 1) / OY, (g.nzl + g.chunk - 1) / g.chunk);
+    const int ox = TX - 2, oy = g.tile_rows - 2;
+    grid = dim3((g.nx + ox - 1) / ox, (g.ny + oy - 1) / oy, (g.nzl + g.chunk - 1) / g.chunk);
     return (int)(grid.x * grid.y * grid.z);
 }
 
@@ -465,12 +163,16 @@ int sg_setup(mm_handle *h) {
     MM_CUDA(cudaMemsetAsync(g.minv, 0, bytes, h->stream));
     MM_CUDA(cudaMalloc(&g.type, g.npad));
     MM_CUDA(cudaMalloc(&g.d_sc, sizeof(StepConsts)));
+    MM_CUDA(cudaMalloc(&g.d_sp, sizeof(SParams)));
+    MM_CUDA(cudaMemcpyAsync(g.d_sp, &g.sp, sizeof(SParams), cudaMemcpyHostToDevice, h->stream));
+    MM_CUDA(cudaStreamSynchronize(h->stream));
     MM_CUDA(cudaHostAlloc(&g.h_sc, sizeof(StepConsts), cudaHostAllocDefault));
     // chunk length along z: enough blocks for >= 4 waves of one block per SM, but no shorter than 8 planes
     dim3 grid;
     g.chunk = 32;
     while (g.chunk > 8 && sg_blocks(h, grid) < 4 * h->num_sms) g.chunk /= 2;
     g.nblocks = sg_blocks(h, grid);
+    g.nblocks_alloc = g.nblocks;
     MM_CUDA(cudaMalloc(&g.d_partials, sizeof(double) * (size_t)g.nblocks * kRedSlots));
     k_type_to_soa<<<grid_for(h, h->ncells, 256), 256, 0, h->stream>>>(h->d_cell_info, g.type, g.nx, g.ny, g.nzl);
     k_halo_u8<<<grid_for(h, g.plane, 256), 256, 0, h->stream>>>(g.type, g.plane, g.nzl);
@@ -491,6 +193,7 @@ void sg_free(mm_handle *h) {
     cudaFree(g.minv);
     cudaFree(g.type);
     cudaFree(g.d_sc);
+    cudaFree(g.d_sp);
     cudaFree(g.d_partials);
     if (g.h_sc) cudaFreeHost(g.h_sc);
     g.active = 0;
@@ -588,57 +291,85 @@ static void fill_args(mm_handle *h, MarchArgs &a) {
     a.minv = g.minv;
     a.type = g.type;
     a.sc = g.d_sc;
+    a.spd = g.d_sp;
     a.partials = g.d_partials;
 }
 
-// Force evaluation at the stored positions (x Rpend).  write_g: store the node gradient into the CURRENT g set.
-int sg_force(mm_handle *h, bool write_g) {
-    SGrid &g = h->sg;
-    MarchArgs a;
-    fill_args(h, a);
-    for (int d = 0; d < 3; d++) a.go[d] = g.g[g.cg][d];  // FORCE mode never reads g: write in place
+template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, bool AHG, int TY>
+static int launch_one(mm_handle *h, const MarchArgs &a, int write_g) {
     dim3 grid;
     sg_blocks(h, grid);
-    const dim3 block(TX, TY);
-    const bool single = g.sp.ntypes == 1 && g.sp.nstates[0] == 1;
     prof_begin(h);
-    if (single) {
-        if (write_g) k_march<false, true, true><<<grid, block, 0, h->stream>>>(g.sp, a);
-        else k_march<false, false, true><<<grid, block, 0, h->stream>>>(g.sp, a);
-    } else {
-        if (write_g) k_march<false, true, false><<<grid, block, 0, h->stream>>>(g.sp, a);
-        else k_march<false, false, false><<<grid, block, 0, h->stream>>>(g.sp, a);
-    }
+    k_march<STEP, SINGLE, ROT, VM, LEAN, AHG, TY><<<grid, dim3(TX, TY), 0, h->stream>>>(h->sg.sp, a, write_g);
     prof_end(h);
     h->launches++;
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
 
-// Fused kick-drift-force-kick.  Reads the current x, v, g sets, writes the other x and v sets (and g when write_g)
-// and flips them.  Halo planes of what was written are refreshed afterwards by the caller (sg_halo).
-int sg_step(mm_handle *h, bool write_g) {
+template <bool SINGLE, bool AHG>
+static int launch_sel(mm_handle *h, const MarchArgs &a, bool step, int rot, int vm, bool lean, int write_g) {
+    constexpr int TY = 8;
+    if (step) {
+        if (lean) {
+            if (vm == 0) return launch_one<1, SINGLE, 0, 0, true, AHG, TY>(h, a, write_g);
+            return launch_one<1, SINGLE, 0, 1, true, AHG, TY>(h, a, write_g);
+        }
+        if (vm == 0) return launch_one<1, SINGLE, 0, 0, false, AHG, TY>(h, a, write_g);
+        if (vm == 1) return launch_one<1, SINGLE, 0, 1, false, AHG, TY>(h, a, write_g);
+        return launch_one<1, SINGLE, 0, 2, false, AHG, TY>(h, a, write_g);
+    }
+    if (rot == 0) return launch_one<0, SINGLE, 0, 0, false, AHG, TY>(h, a, write_g);
+    if (rot == 1) return launch_one<0, SINGLE, 1, 0, false, AHG, TY>(h, a, write_g);
+    return launch_one<0, SINGLE, 2, 0, false, AHG, TY>(h, a, write_g);
+}
+
+static int launch_march(mm_handle *h, const MarchArgs &a, bool step, int rot, int vm, bool lean, int write_g) {
+    const bool single = h->sg.sp.ntypes == 1 && h->sg.sp.nstates[0] == 1;
+    if (!single) return launch_sel<false, false>(h, a, step, rot, vm, false, write_g);
+    if (h->sg.ahg) return launch_sel<true, true>(h, a, step, rot, vm, lean, write_g);
+    return launch_sel<true, false>(h, a, step, rot, vm, lean, write_g);
+}
+
+// Force evaluation at the stored positions.  rot: 0 = positions are true as stored, 1 = apply the pending rotation
+// Rpend on load, 2 = apply it and write the rotated positions to the other x set (which becomes current).
+// write_g: store the node gradient into the CURRENT g set (FORCE mode never reads g).
+int sg_force(mm_handle *h, bool write_g, int rot) {
     SGrid &g = h->sg;
     MarchArgs a;
     fill_args(h, a);
-    dim3 grid;
-    sg_blocks(h, grid);
-    const dim3 block(TX, TY);
-    const bool single = g.sp.ntypes == 1 && g.sp.nstates[0] == 1;
-    prof_begin(h);
-    if (single) {
-        if (write_g) k_march<true, true, true><<<grid, block, 0, h->stream>>>(g.sp, a);
-        else k_march<true, false, true><<<grid, block, 0, h->stream>>>(g.sp, a);
-    } else {
-        if (write_g) k_march<true, true, false><<<grid, block, 0, h->stream>>>(g.sp, a);
-        else k_march<true, false, false><<<grid, block, 0, h->stream>>>(g.sp, a);
-    }
-    prof_end(h);
-    h->launches++;
+    for (int d = 0; d < 3; d++) a.go[d] = g.g[g.cg][d];
+    const int rc = launch_march(h, a, false, rot, 0, false, write_g ? 1 : 0);
+    if (rot == 2) g.cx ^= 1;
+    return rc;
+}
+
+// Fused kick-drift-force-kick.  Reads the current x, v, g sets, writes the other x and v sets (and g when write_g)
+// and flips them.  vm: pending velocity transform 0 none / 1 scalar / 2 matrix.  The halo planes of what was
+// written are refreshed afterwards by the caller (sg_halo).
+int sg_step(mm_handle *h, bool write_g, int vm, bool lean) {
+    SGrid &g = h->sg;
+    MarchArgs a;
+    fill_args(h, a);
+    const int rc = launch_march(h, a, true, 0, vm, lean && vm != 2, write_g ? 1 : 0);
     g.cx ^= 1;
     g.cv ^= 1;
     if (write_g) g.cg ^= 1;
-    MM_CUDA(cudaGetLastError());
+    return rc;
+}
+
+int sg_set_tile_rows(mm_handle *h, int rows) {
+    SGrid &g = h->sg;
+    if (rows != 8) return MM_ERR_INVALID;
+    g.tile_rows = rows;
+    dim3 grid;
+    const int nb = sg_blocks(h, grid);
+    if (nb > g.nblocks_alloc) {
+        cudaFree(g.d_partials);
+        MM_CUDA(cudaMalloc(&g.d_partials, sizeof(double) * (size_t)nb * kRedSlots));
+        g.nblocks_alloc = nb;
+    }
+    g.nblocks = nb;
     return MM_OK;
 }
 

@@ -53,9 +53,12 @@ struct SGrid {
     uint8_t *type = nullptr;
     int cx = 0, cv = 0, cg = 0;     // which copy is current
     StepConsts *d_sc = nullptr;
+    SParams *d_sp = nullptr;        // device copy of sp
     StepConsts *h_sc = nullptr;     // pinned staging
     double *d_partials = nullptr;   // [nblocks][kRedSlots]
-    int nblocks = 0;
+    int nblocks = 0, nblocks_alloc = 0;
+    int tile_rows = 8;              // TY of the marching kernel (warps per block)
+    int ahg = 0;                    // tuning: elasticity block via global loads instead of uniform registers
     int chunk = 32;                 // owned planes per block along z
     SParams sp;
 };
@@ -71,6 +74,7 @@ struct MarchArgs {
     const double *m, *minv;
     const uint8_t *type;
     const StepConsts *sc;
+    const SParams *spd;  // the same parameters in global memory (for the non-hoistable elasticity loads)
     double *partials;
 };
 
