@@ -249,26 +249,34 @@ def main():
     _lib.check(lib.mm_set_option(part.handle, b"profile", 1))
     nprof = max(3, min(args.steps, 10))
     _lib.check(lib.mm_md_run(md, nprof))
-    nl, tot = ctypes.c_int64(), ctypes.c_double()
-    _lib.check(lib.mm_profile(part.handle, ctypes.byref(nl), ctypes.byref(tot)))
+    nl, tot = (ctypes.c_int64 * 2)(), (ctypes.c_double * 2)()
+    _lib.check(lib.mm_profile(part.handle, nl, tot))
     _lib.check(lib.mm_set_option(part.handle, b"profile", 0))
-    kernel_ms = tot.value / max(nl.value, 1)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    fused = bool(getattr(part, "fused_step", False))
-    bytes_per_launch = (BYTES_PER_NODE_STEP if fused else BYTES_PER_NODE_EVAL) * nnodes
-    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    # dominant kernel: the fused kick-drift-force-kick launch when the structured path is active (kind 1), else the
+    # per-cell force kernel of the indexed path (kind 0).  Algorithmic bytes: SURVEY.md 8(d), per node and launch.
+    fused = nl[1] > 0
+    if fused:
+        kernel_ms, name, bpn = tot[1] / nl[1], "k_march<STEP> (fused kick-drift-force-kick, structured grid)", BYTES_PER_NODE_STEP
+    else:
+        kernel_ms, name, bpn = tot[0] / max(nl[0], 1), "k_cells (per-cell force kernel, indexed topology)", BYTES_PER_NODE_EVAL
+    achieved = bpn * nnodes / (kernel_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-        "kernel": "fused force+Verlet step" if fused else "k_cells (per-cell force kernel)",
-        "bytes_per_node": BYTES_PER_NODE_STEP if fused else BYTES_PER_NODE_EVAL, "kernel_ms": kernel_ms,
-        "launches_timed": int(nl.value), "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
+        "kernel": name, "bytes_per_node": bpn, "kernel_ms": kernel_ms, "launches_timed": int(nl[1] if fused else nl[0]),
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
+        # whole step against the survey's convention of 108 B per node and force evaluation
         "step_frac_of_108B_roofline": (BYTES_PER_NODE_STEP * FORCE_EVALS[args.ensemble] * nnodes * args.steps / (ms * 1e-3) / 1e9) / peak,
     }
+    if fused and nl[0] > 0:  # the force-only launches of the barostat (52 B/node algorithmic)
+        fms = tot[0] / nl[0]
+        roofline["force_only_kernel"] = {"kernel": "k_march<FORCE>", "kernel_ms": fms, "bytes_per_node": BYTES_PER_NODE_EVAL,
+                                         "achieved": BYTES_PER_NODE_EVAL * nnodes / (fms * 1e-3) / 1e9, "launches_timed": int(nl[0])}
 
     # ---- e2e: host buffers in, one step, host buffers out, every step ---------------------------------------------
     e2e = None

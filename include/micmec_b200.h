@@ -103,9 +103,9 @@ int mm_synchronize(mm_handle *h);
 /* options: "scatter" 0 = node-centric gather (deterministic) / 1 = cell-centric warp-aggregated atomic scatter for
  * the gpos accumulation of the structured path; "profile" 1 = bracket every force kernel with CUDA events */
 int mm_set_option(mm_handle *h, const char *name, int64_t value);
-/* with "profile" on: number of force-kernel launches timed since the last call and their summed device time (ms);
- * synchronises the stream and resets the counters */
-int mm_profile(mm_handle *h, int64_t *nlaunch, double *total_ms);
+/* with "profile" on: launches timed since the last call and their summed device time (ms), separately for
+ * [0] force-only kernels and [1] fused kick-drift-force-kick kernels; synchronises the stream and resets the counters */
+int mm_profile(mm_handle *h, int64_t nlaunch[2], double total_ms[2]);
 
 /* ---- Domain  (micmec/pes/ext.pyx:36-123 + micmec/pes/domain.c:13-71) ------------------------------------ */
 /* rvecs [nvec][3]; writes volume (domain.c:23-48) and the reciprocal vectors gvecs [nvec][3] (ext.pyx:64-71) */

@@ -99,7 +99,7 @@ def load():
     lib.mm_set_stream.argtypes = [vp, vp]
     lib.mm_synchronize.argtypes = [vp]
     lib.mm_set_option.argtypes = [vp, ctypes.c_char_p, i64]
-    lib.mm_profile.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(dbl)]
+    lib.mm_profile.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(dbl)]  # int64[2], double[2]
     lib.mm_domain.argtypes = [vp, i32, ctypes.POINTER(dbl), vp]
     lib.mm_md_create.argtypes = [vp, ctypes.POINTER(MDDesc), ctypes.POINTER(vp)]
     lib.mm_md_destroy.argtypes = [vp]

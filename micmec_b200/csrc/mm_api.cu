@@ -353,17 +353,20 @@ int mm_profile(mm_handle *h, int64_t *nlaunch, double *total_ms) {
     if (!h || !nlaunch || !total_ms) return invalid("mm_profile: null argument");
     MM_CUDA(cudaSetDevice(h->device));
     MM_CUDA(cudaStreamSynchronize(h->stream));
-    double total = 0.0;
-    for (auto &ev : h->prof_events) {
+    nlaunch[0] = nlaunch[1] = 0;
+    total_ms[0] = total_ms[1] = 0.0;
+    for (size_t i = 0; i < h->prof_events.size(); i++) {
+        auto &ev = h->prof_events[i];
         float ms = 0.0f;
         MM_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
-        total += ms;
+        const int kind = h->prof_kinds[i] ? 1 : 0;
+        nlaunch[kind]++;
+        total_ms[kind] += ms;
         cudaEventDestroy(ev.first);
         cudaEventDestroy(ev.second);
     }
-    *nlaunch = (int64_t)h->prof_events.size();
-    *total_ms = total;
     h->prof_events.clear();
+    h->prof_kinds.clear();
     return MM_OK;
 }
 

@@ -107,12 +107,13 @@ int grid_for(const mm_handle *h, int64_t n, int threads) {
 }
 
 // cell kernel only; returns the number of blocks whose partials (energy + virial) now sit in h->d_partials
-void prof_begin(mm_handle *h) {
+void prof_begin(mm_handle *h, int kind) {
     if (!h->profile) return;
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     h->prof_events.emplace_back(a, b);
+    h->prof_kinds.push_back(kind);
     cudaEventRecord(a, h->stream);
 }
 
@@ -123,7 +124,7 @@ void prof_end(mm_handle *h) {
 
 int cells_launch(mm_handle *h) {
     const int gc = grid_for(h, h->ncells, kThreads);
-    prof_begin(h);
+    prof_begin(h, 0);
     if (h->model == MM_MODEL_ORIGINAL)
         k_cells<MM_MODEL_ORIGINAL><<<gc, kThreads, 0, h->stream>>>(h->kp, h->d_cell_nodes, h->d_cell_info, h->d_pos,
                                                                    h->d_rvecs, h->ncells, h->d_gcell, h->d_ecell,

@@ -66,6 +66,7 @@ struct mm_handle {
     int scatter_mode = 0;
     int profile = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // one pair per timed force-kernel launch
+    std::vector<int> prof_kinds;
     bool pos_valid = false;
     int want_structured = 1;  // use the structured-grid kernels when the system allows it
     mm::SGrid sg;
@@ -82,7 +83,7 @@ int grid_for(const mm_handle *h, int64_t n, int threads);
 // cell kernel only; returns the number of blocks whose partials (energy + virial) were written to h->d_partials
 int cells_launch(mm_handle *h);
 // event bracket around the dominant kernel when h->profile is on
-void prof_begin(mm_handle *h);
+void prof_begin(mm_handle *h, int kind);  // kind 0: force-only kernel, 1: fused step kernel
 void prof_end(mm_handle *h);
 void final_launch(mm_handle *h, const double *pc, int nbc, const double *pn, int nbn);
 

@@ -299,7 +299,7 @@ template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, bool AHG, int TY>
 static int launch_one(mm_handle *h, const MarchArgs &a, int write_g) {
     dim3 grid;
     sg_blocks(h, grid);
-    prof_begin(h);
+    prof_begin(h, STEP);
     k_march<STEP, SINGLE, ROT, VM, LEAN, AHG, TY><<<grid, dim3(TX, TY), 0, h->stream>>>(h->sg.sp, a, write_g);
     prof_end(h);
     h->launches++;
