@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "MD node-steps/s (force+Verlet, fp64)", "value": rate, "unit": "node-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, world),
         "cpu_baseline": {"value": rate, "unit": "node-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "node-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -165,8 +165,8 @@ def workload_config(args, world):
         "workload": "synthetic %dx%dx%d-cell fcu grid %s MD (%s), dt 10 fs" % (
             args.grid, args.grid, args.grid, args.ensemble.upper(),
             {"nve": "velocity Verlet", "nvt": "NHC thermostat", "npt": "NHC thermostat + MTK barostat"}[args.ensemble]),
-        "nodes_per_gpu": args.grid ** 3, "force_evals_per_step": FORCE_EVALS[args.ensemble], "model": args.model,
-        "parallelism": "single GPU" if world == 1 else "independent replicas x%d" % world,
+        "nodes_total": args.grid ** 3, "nodes_per_gpu": args.grid ** 3 // world, "force_evals_per_step": FORCE_EVALS[args.ensemble], "model": args.model,
+        "parallelism": "single GPU" if world == 1 else "%d z-slabs (one per GPU), NCCL halo planes + 16-double all-reduce" % world,
         "cache": "inputs larger than L2 (pos/vel/gpos %.0f MB each)" % (24.0 * args.grid ** 3 / 1e6),
     }
 
@@ -193,10 +193,27 @@ def main():
     from micmec_b200.sampling.npt import MTKBarostat, TBCombination
 
     lib = _lib.load()
-    system, vel0 = make_state(args.grid, seed=rank)
-    nnodes = system.nnodes
     p = md_params(args.ensemble)
-    part = ForcePartMechanical(system, model=args.model, device=local_rank, structured=False if args.generic else None)
+    ndof = None
+    if world == 1:
+        system, vel0 = make_state(args.grid, seed=rank)
+        nnodes = nglobal = system.nnodes
+        part = ForcePartMechanical(system, model=args.model, device=local_rank, structured=False if args.generic else None)
+    else:
+        # strong scaling: the SAME G^3 grid cut into `world` z-slabs, one per GPU; every rank generates only its slab
+        from micmec_b200 import slab as slabmod
+        from micmec_b200.celltypes import TYPE_FCU
+        from micmec_b200.units import boltzmann
+
+        layout = slabmod.SlabLayout((args.grid,) * 3, rank, world)
+        system = slabmod.local_system(layout, TYPE_FCU)
+        rng = np.random.default_rng(1000 + rank)
+        system.pos += 0.1 * rng.standard_normal(system.pos.shape)
+        vel0 = rng.standard_normal(system.pos.shape) * np.sqrt(boltzmann * 300.0 / system.masses)[:, None]
+        vel0 -= vel0.mean(axis=0)
+        nnodes, nglobal = system.nnodes, layout.nnodes_global
+        ndof = 3 * nglobal - (3 if (p["thermo"] or p["baro"]) else 0)
+        part = ForcePartMechanical(system, model=args.model, device=local_rank, slab=layout.slab_arg())
     if args.tile_rows:
         _lib.check(lib.mm_set_option(part.handle, b"tile_rows", args.tile_rows))
     if args.ahg >= 0:
@@ -204,6 +221,8 @@ def main():
     mmf = MicMecForceField(system, [part])
     stream = torch.cuda.Stream(device=local_rank)
     _lib.check(lib.mm_set_stream(part.handle, ctypes.c_void_p(stream.cuda_stream)))
+    if world > 1:
+        slabmod.init_comm(part, layout)
     hooks = []
     thermo = baro = None
     if p["thermo"]:
@@ -214,7 +233,7 @@ def main():
         hooks.append(TBCombination(thermo, baro))
     elif thermo is not None:
         hooks.append(thermo)
-    verlet = VerletIntegrator(mmf, timestep=p["timestep"], hooks=hooks, vel0=vel0)
+    verlet = VerletIntegrator(mmf, timestep=p["timestep"], hooks=hooks, vel0=vel0, ndof=ndof)
     assert verlet.device_mode
     md = verlet._md
 
@@ -241,7 +260,7 @@ def main():
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * nnodes * args.steps / (ms * 1e-3)
+    value = nglobal * args.steps / (ms * 1e-3)
     scal = np.zeros(_lib.S_COUNT)
     _lib.check(lib.mm_md_scalars(md, _lib.ptr(scal)))  # raises on NaN: a diverged run is not a measurement
 
@@ -300,7 +319,7 @@ def main():
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": world * nnodes * esteps / dt, "unit": "node-steps/s", "h2d_bytes_per_step": 48 * nnodes,
+        e2e = {"value": nglobal * esteps / dt, "unit": "node-steps/s", "h2d_bytes_per_step": 48 * nnodes,
                "d2h_bytes_per_step": 48 * nnodes + 8 * _lib.S_COUNT, "steps": esteps,
                "api": "mm_md_set_state(host) + mm_md_run(1) + mm_md_get_state(host) + mm_md_scalars per step"}
 
@@ -317,7 +336,7 @@ def main():
         line = {
             "metric": "MD node-steps/s (force+Verlet, fp64)", "value": value, "unit": "node-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
             "force_evals_per_s": value * FORCE_EVALS[args.ensemble],

@@ -72,6 +72,12 @@ typedef struct {
      * reference enumeration id = (k*ny + l)*nz + m (micmec/utils.py:113-137,150-161).  The index arrays above may
      * then be NULL (they are implied) - this is how the 64^3 / 256^3 grids are built without O(N^6) host work. */
     int32_t nx, ny, nz;
+    /* z-slab decomposition over the GPUs of one box (one process per GPU): with slab_count > 1 this handle owns the
+     * nz planes [slab_rank * nz, (slab_rank + 1) * nz) of a grid that is slab_count * nz planes tall; nnodes / ncells
+     * are the LOCAL counts, nnodes_global the total.  Arrays passed to / returned by this handle are the local slab in
+     * reference order (id = (k*ny + l)*nz + m_local).  Needs mm_comm_init before the first compute. */
+    int32_t slab_rank, slab_count;
+    int64_t nnodes_global;
 } mm_desc;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
@@ -106,6 +112,15 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value);
 /* with "profile" on: launches timed since the last call and their summed device time (ms), separately for
  * [0] force-only kernels and [1] fused kick-drift-force-kick kernels; synchronises the stream and resets the counters */
 int mm_profile(mm_handle *h, int64_t nlaunch[2], double total_ms[2]);
+
+/* ---- multi-GPU (no reference counterpart: the reference is single-process) ---------------------------------- */
+/* NCCL bootstrap: rank 0 creates a 128-byte unique id, the host side broadcasts it (torch.distributed), every rank
+ * calls mm_comm_init.  nccl_path: the libnccl.so.2 to dlopen (NULL: the one already loaded in the process).
+ * Afterwards halo planes travel with ncclSend/ncclRecv and the <= 16 reduced doubles with ncclAllReduce, all on the
+ * handle's stream, inside mm_compute / mm_md_run. */
+int mm_comm_unique_id(const char *nccl_path, char *out128);
+int mm_comm_init(mm_handle *h, const char *nccl_path, const char *id128);
+int mm_comm_destroy(mm_handle *h);
 
 /* ---- Domain  (micmec/pes/ext.pyx:36-123 + micmec/pes/domain.c:13-71) ------------------------------------ */
 /* rvecs [nvec][3]; writes volume (domain.c:23-48) and the reciprocal vectors gvecs [nvec][3] (ext.pyx:64-71) */

@@ -77,6 +77,25 @@ __global__ void k_grid_topology(int nx, int ny, int nz, int32_t *cell_nodes, int
     }
 }
 
+// Index arrays and per-cell buffers of the indexed kernels, built on first use for structured grids (they cost
+// 256 B per node, which the structured path never touches).
+int ensure_generic(mm_handle *h) {
+    if (h->d_cell_nodes) return MM_OK;
+    if (h->slab_count > 1) {
+        set_error("the indexed-topology kernels are not available on a z-slab of a decomposed grid");
+        return MM_ERR_STATE;
+    }
+    const int64_t nc = h->ncells, nn = h->nnodes;
+    MM_CUDA(cudaMalloc(&h->d_cell_nodes, sizeof(int32_t) * 8 * nc));
+    MM_CUDA(cudaMalloc(&h->d_node_cells, sizeof(int32_t) * 8 * nn));
+    MM_CUDA(cudaMalloc(&h->d_gcell, sizeof(double) * 24 * nc));
+    MM_CUDA(cudaMalloc(&h->d_ecell, sizeof(double) * nc));
+    k_grid_topology<<<grid_for(h, nc, 256), 256, 0, h->stream>>>(h->nx, h->ny, h->nz, h->d_cell_nodes, h->d_node_cells,
+                                                                  h->d_cell_info, nc);
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+
 }  // namespace mm
 
 using namespace mm;
@@ -117,6 +136,8 @@ int mm_destroy(mm_handle *h) {
     cudaFree(h->d_partials);
     cudaFree(h->d_result);
     cudaFree(h->d_rvecs);
+    cudaFree(h->d_red);
+    mm_comm_destroy(h);
     if (h->sg.active || h->sg.d_sc) sg_free(h);
     if (h->h_result) cudaFreeHost(h->h_result);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -139,6 +160,12 @@ int mm_create(const mm_desc *desc, mm_handle **out) {
             return invalid("mm_create: structured grid needs ncells == nnodes == nx*ny*nz");
         if (desc->nx < 2 || desc->ny < 2 || desc->nz < 2)
             return invalid("mm_create: a periodic axis needs at least 2 cells (1-wide axes are degenerate in the reference)");
+        if (desc->slab_count > 1 && (desc->slab_rank < 0 || desc->slab_rank >= desc->slab_count))
+            return invalid("mm_create: slab_rank out of range");
+        if (desc->slab_count > 1 && desc->model != MM_MODEL_ORIGINAL)
+            return invalid("mm_create: the slab decomposition runs on the structured-grid kernels (model 'original')");
+    } else if (desc->slab_count > 1) {
+        return invalid("mm_create: the slab decomposition needs a structured grid (nx, ny, nz)");
     } else if (!desc->surrounding_nodes || !desc->surrounding_cells || !desc->shift) {
         return invalid("mm_create: index arrays are required for a non-structured system");
     }
@@ -156,6 +183,9 @@ int mm_create(const mm_desc *desc, mm_handle **out) {
     h->nx = desc->nx;
     h->ny = desc->ny;
     h->nz = desc->nz;
+    h->slab_count = desc->slab_count > 1 ? desc->slab_count : 1;
+    h->slab_rank = desc->slab_count > 1 ? desc->slab_rank : 0;
+    h->nnodes_global = desc->nnodes_global > 0 ? desc->nnodes_global : desc->nnodes * h->slab_count;
 
     // ---- parameters (mmff.py:219-231) -----------------------------------------------------------------------
     memset(&h->kp, 0, sizeof(h->kp));
@@ -259,13 +289,15 @@ int mm_create(const mm_desc *desc, mm_handle **out) {
     h->num_sms = prop.multiProcessorCount;
     MM_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
-    MM_TRY(cudaMalloc(&h->d_cell_nodes, sizeof(int32_t) * 8 * nc));
-    MM_TRY(cudaMalloc(&h->d_node_cells, sizeof(int32_t) * 8 * nn));
+    if (!structured) {  // structured grids build these on first use of the indexed kernels (ensure_generic)
+        MM_TRY(cudaMalloc(&h->d_cell_nodes, sizeof(int32_t) * 8 * nc));
+        MM_TRY(cudaMalloc(&h->d_node_cells, sizeof(int32_t) * 8 * nn));
+        MM_TRY(cudaMalloc(&h->d_gcell, sizeof(double) * 24 * nc));
+        MM_TRY(cudaMalloc(&h->d_ecell, sizeof(double) * nc));
+    }
     MM_TRY(cudaMalloc(&h->d_cell_info, nc));
     MM_TRY(cudaMalloc(&h->d_pos, sizeof(double) * 3 * nn));
     MM_TRY(cudaMalloc(&h->d_gpos, sizeof(double) * 3 * nn));
-    MM_TRY(cudaMalloc(&h->d_gcell, sizeof(double) * 24 * nc));
-    MM_TRY(cudaMalloc(&h->d_ecell, sizeof(double) * nc));
     MM_TRY(cudaMalloc(&h->d_partials, sizeof(double) * 2 * kMaxRedBlocks * kRedSlots));
     MM_TRY(cudaMalloc(&h->d_result, sizeof(ForceResult)));
     MM_TRY(cudaMalloc(&h->d_rvecs, sizeof(double) * 9));
@@ -273,18 +305,14 @@ int mm_create(const mm_desc *desc, mm_handle **out) {
     MM_TRY(cudaMemsetAsync(h->d_rvecs, 0, sizeof(double) * 9, h->stream));
     MM_TRY(cudaMemsetAsync(h->d_gpos, 0, sizeof(double) * 3 * nn, h->stream));
     MM_TRY(cudaMemcpyAsync(h->d_cell_info, info.data(), nc, cudaMemcpyHostToDevice, h->stream));
-    if (structured) {
-        MM_TRY(cudaStreamSynchronize(h->stream));
-        k_grid_topology<<<grid_for(h, nc, 256), 256, 0, h->stream>>>(h->nx, h->ny, h->nz, h->d_cell_nodes,
-                                                                      h->d_node_cells, h->d_cell_info, nc);
-        MM_TRY(cudaGetLastError());
-    } else {
+    if (!structured) {
         MM_TRY(cudaMemcpyAsync(h->d_cell_nodes, cn.data(), sizeof(int32_t) * 8 * nc, cudaMemcpyHostToDevice, h->stream));
         MM_TRY(cudaMemcpyAsync(h->d_node_cells, ncell.data(), sizeof(int32_t) * 8 * nn, cudaMemcpyHostToDevice, h->stream));
     }
     MM_TRY(cudaStreamSynchronize(h->stream));
 #undef MM_TRY
-    if (sg_eligible(h) && h->nnodes >= 4096) {  // small grids are launch-bound either way: keep them on the simple path
+    // small grids are launch-bound either way: keep them on the simple path (slabs always use the structured kernels)
+    if (sg_eligible(h) && (h->nnodes >= 4096 || h->slab_count > 1)) {
         const int rc = sg_setup(h);
         if (rc != MM_OK) {
             mm_destroy(h);
@@ -404,8 +432,12 @@ int mm_compute(mm_handle *h, double *energy_host, double *gpos, int where, doubl
         return MM_ERR_STATE;
     }
     MM_CUDA(cudaSetDevice(h->device));
-    const int rc = force_evaluate(h, gpos ? h->d_gpos : nullptr, gpos != nullptr);
+    int rc = force_evaluate(h, gpos ? h->d_gpos : nullptr, gpos != nullptr);
     if (rc != MM_OK) return rc;
+    if (h->slab_count > 1) {  // energy, virial and sum g^2 of the whole grid
+        rc = comm_allreduce(h, reinterpret_cast<double *>(h->d_result), 8);
+        if (rc != MM_OK) return rc;
+    }
     MM_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, sizeof(ForceResult), cudaMemcpyDeviceToHost, h->stream));
     if (gpos && gpos != h->d_gpos)
         MM_CUDA(cudaMemcpyAsync(gpos, h->d_gpos, sizeof(double) * 3 * h->nnodes,
@@ -443,6 +475,11 @@ int mm_get_cell_cache(mm_handle *h, double *epot_cells, double *gpos_cells) {
     if (!h) return invalid("mm_get_cell_cache: null handle");
     MM_CUDA(cudaSetDevice(h->device));
     const int64_t nc = h->ncells;
+    if (h->sg.active) {  // the structured kernels never materialise per-cell data: produce it on demand
+        const int rc = ensure_generic(h);
+        if (rc != MM_OK) return rc;
+        cells_launch(h);
+    }
     if (epot_cells)
         MM_CUDA(cudaMemcpyAsync(epot_cells, h->d_ecell, sizeof(double) * nc, cudaMemcpyDeviceToHost, h->stream));
     if (gpos_cells) {

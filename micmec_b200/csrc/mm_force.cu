@@ -155,6 +155,10 @@ int force_evaluate(mm_handle *h, double *gpos_out, bool want_g2) {
         MM_CUDA(cudaGetLastError());
         return MM_OK;
     }
+    {
+        const int rc = ensure_generic(h);
+        if (rc != MM_OK) return rc;
+    }
     double *pn = h->d_partials + (size_t)kMaxRedBlocks * kRedSlots;
     const int gc = cells_launch(h);
     int gn = 0;

@@ -69,6 +69,11 @@ struct mm_handle {
     std::vector<int> prof_kinds;
     bool pos_valid = false;
     int want_structured = 1;  // use the structured-grid kernels when the system allows it
+    // z-slab decomposition (mm_comm.cu): this handle owns nz planes of a grid that is slab_count slabs tall
+    int slab_rank = 0, slab_count = 1;
+    int64_t nnodes_global = 0;
+    void *comm = nullptr;     // ncclComm_t
+    double *d_red = nullptr;  // [32] reduction buffer all-reduced across the slabs
     mm::SGrid sg;
 };
 
@@ -82,6 +87,8 @@ int force_evaluate(mm_handle *h, double *gpos_out, bool want_g2);
 int grid_for(const mm_handle *h, int64_t n, int threads);
 // cell kernel only; returns the number of blocks whose partials (energy + virial) were written to h->d_partials
 int cells_launch(mm_handle *h);
+// index arrays / per-cell buffers of the indexed kernels (built lazily for structured grids; mm_api.cu)
+int ensure_generic(mm_handle *h);
 // event bracket around the dominant kernel when h->profile is on
 void prof_begin(mm_handle *h, int kind);  // kind 0: force-only kernel, 1: fused step kernel
 void prof_end(mm_handle *h);
@@ -100,5 +107,10 @@ int sg_to_aos(mm_handle *h, int which, double *d_aos);
 int sg_force(mm_handle *h, bool write_g, int rot);
 int sg_step(mm_handle *h, bool write_g, int vm, bool lean);
 int sg_set_tile_rows(mm_handle *h, int rows);
+
+// ---- mm_comm.cu ---------------------------------------------------------------------------------------------
+int comm_halo(mm_handle *h, double **fields, int nfields, int npos);
+int comm_allreduce(mm_handle *h, double *buf, int count);
+int comm_reduce_partials(mm_handle *h, const double *pc, int nbc, const double *pn, int nbn, const double *pd, int nbd);
 
 }  // namespace mm

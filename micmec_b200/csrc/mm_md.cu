@@ -294,6 +294,9 @@ __device__ void properties(MDState &s, double n3) {  // verlet.py:171-190
 
 // One block.  Sums the block partials it is told to consume, then thread 0 runs the requested sub-steps in the
 // canonical order RESET_MVEL, TAKE_FORCE, TAKE_KIN, BARO_B, THERMO, BARO_A, ECONS, PROPS (see md_step below).
+__device__ void scalar_ops(MDState &s, double *rvecs_dev, StepConsts *sc, unsigned ops, const double *fr, const double *kn,
+                           const double *dl, int nbn, double n3);
+
 __global__ void __launch_bounds__(256)
 k_scalar(MDState *st, double *rvecs_dev, StepConsts *sc, unsigned ops, const double *pc, int nbc, const double *pn, int nbn,
          const double *pd, int nbd, double n3) {
@@ -301,8 +304,22 @@ k_scalar(MDState *st, double *rvecs_dev, StepConsts *sc, unsigned ops, const dou
     if (ops & OP_TAKE_FORCE) partials_sum<7>(pc, nbc, kRedSlots, fr);
     if ((ops & (OP_TAKE_KIN | OP_TAKE_FORCE)) && nbn > 0) partials_sum<7>(pn, nbn, kRedSlots, kn);
     if ((ops & OP_TAKE_DELTA) && nbd > 0) partials_sum<1>(pd, nbd, kRedSlots, dl);
-    if (threadIdx.x != 0) return;
-    MDState &s = *st;
+    // Work on a shared-memory copy of the state: the serial algebra below touches a few hundred fields, and as
+    // dependent global-memory accesses they cost ~30 us per launch; from shared memory it is a few.
+    __shared__ MDState sm_state;
+    static_assert(sizeof(MDState) % sizeof(double) == 0, "MDState is copied as doubles");
+    constexpr int kWords = sizeof(MDState) / sizeof(double);
+    for (int i = threadIdx.x; i < kWords; i += blockDim.x)
+        reinterpret_cast<double *>(&sm_state)[i] = reinterpret_cast<const double *>(st)[i];
+    __syncthreads();
+    if (threadIdx.x == 0) scalar_ops(sm_state, rvecs_dev, sc, ops, fr, kn, dl, nbn, n3);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWords; i += blockDim.x)
+        reinterpret_cast<double *>(st)[i] = reinterpret_cast<const double *>(&sm_state)[i];
+}
+
+__device__ void scalar_ops(MDState &s, double *rvecs_dev, StepConsts *sc, unsigned ops, const double *fr, const double *kn,
+                           const double *dl, int nbn, double n3) {
     if (ops & OP_RESET_MVEL)
         for (int i = 0; i < 9; i++) s.Mvel[i] = (i % 4 == 0) ? 1.0 : 0.0;
     if (ops & OP_POS_WRITTEN)  // the stored positions are the true ones again
@@ -538,8 +555,21 @@ static int scalar_launch(mm_md *md, unsigned ops, int nbc, int nbn, int nbd) {
     // structured kernels leave all 14 sums of a block in one partial: energy + virial in slots 0-6, moments + g^2 in 7-13
     const double *pc = sg ? h->sg.d_partials : h->d_partials;
     const double *pn = sg ? h->sg.d_partials + 7 : md->d_pkin;
-    k_scalar<<<1, 256, 0, h->stream>>>(md->d_state, h->d_rvecs, sg ? h->sg.d_sc : nullptr, ops, pc, nbc, pn, nbn,
-                                       md->d_pdelta, nbd, 3.0 * (double)h->nnodes);
+    const double *pd = md->d_pdelta;
+    if (h->slab_count > 1 && (nbc > 0 || nbn > 0 || nbd > 0)) {
+        // z-slabs: sum the local partials, all-reduce the 16 doubles, and hand the scalar kernel ONE "block" of sums.
+        // Every rank then runs the same scalar algebra on bit-identical inputs.
+        const int rc = comm_reduce_partials(h, pc, nbc, pn, nbn, pd, nbd);
+        if (rc != MM_OK) return rc;
+        pc = h->d_red;
+        pn = h->d_red + 7;
+        pd = h->d_red + 14;
+        nbc = nbc > 0 ? 1 : 0;
+        nbn = nbn > 0 ? 1 : 0;
+        nbd = nbd > 0 ? 1 : 0;
+    }
+    k_scalar<<<1, 256, 0, h->stream>>>(md->d_state, h->d_rvecs, sg ? h->sg.d_sc : nullptr, ops, pc, nbc, pn, nbn, pd, nbd,
+                                       3.0 * (double)h->nnodes_global);
     h->launches++;
     return MM_OK;
 }
@@ -818,6 +848,8 @@ int mm_md_init(mm_md *md, const double *pos, const double *vel, const double *ma
         md->initialised = true;
         return MM_OK;
     }
+    rc = ensure_generic(h);
+    if (rc != MM_OK) return rc;
     const int nbc = cells_launch(h);
     k_gather_g2<<<gn, kNodeThreads, 0, h->stream>>>(h->d_node_cells, h->d_gcell, nn, h->ncells, h->d_gpos, md->d_pkin);
     h->launches++;

@@ -56,31 +56,53 @@ k_halo_u8(uint8_t *f, int64_t plane, int nzl) {
     }
 }
 
-// reference order (AoS, id = (k*ny + l)*nz + m) <-> z-major SoA planes (owned planes only)
-__global__ void __launch_bounds__(256)
+// reference order (AoS, id = (k*ny + l)*nz + m) <-> z-major SoA planes (owned planes only).
+// Tiled through shared memory: a block handles a 32 (k) x 32 (m) tile of one l row, so that the SoA side is accessed
+// along k (its unit stride) and the AoS side along m (96 consecutive doubles per k) - both sides fully coalesced.
+constexpr int TT = 32;
+
+__global__ void __launch_bounds__(TT * 8)
 k_aos_to_soa(const double *__restrict__ aos, double *s0, double *s1, double *s2, int nx, int ny, int nz) {
-    const int64_t n = (int64_t)nx * ny * nz;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(i % nx), l = (int)((i / nx) % ny), m = (int)(i / ((int64_t)nx * ny));
-        const int64_t src = ((int64_t)k * ny + l) * nz + m;
-        const int64_t dst = i + (int64_t)nx * ny;  // skip the lower halo plane
-        s0[dst] = aos[3 * src];
-        s1[dst] = aos[3 * src + 1];
-        s2[dst] = aos[3 * src + 2];
+    __shared__ double tile[3][TT][TT + 1];  // [d][k][m]
+    const int k0 = blockIdx.x * TT, l = blockIdx.y, m0 = blockIdx.z * TT;
+    const int mt = min(TT, nz - m0), kt = min(TT, nx - k0);
+    const int tid = threadIdx.y * TT + threadIdx.x;
+    for (int kk = 0; kk < kt; kk++) {  // one k row of the tile: 3*mt consecutive doubles of the AoS array
+        const int64_t base = (((int64_t)(k0 + kk) * ny + l) * nz + m0) * 3;
+        for (int j = tid; j < 3 * mt; j += TT * 8) tile[j % 3][kk][j / 3] = aos[base + j];
+    }
+    __syncthreads();
+    double *dst[3] = {s0, s1, s2};
+    const int kk = threadIdx.x;
+    for (int mm = threadIdx.y; mm < mt; mm += 8) {
+        if (kk < kt) {
+            const int64_t at = ((int64_t)(m0 + mm + 1) * ny + l) * nx + k0 + kk;  // +1: skip the lower halo plane
+#pragma unroll
+            for (int d = 0; d < 3; d++) dst[d][at] = tile[d][kk][mm];
+        }
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TT * 8)
 k_soa_to_aos(const double *__restrict__ s0, const double *__restrict__ s1, const double *__restrict__ s2, double *aos,
              int nx, int ny, int nz) {
-    const int64_t n = (int64_t)nx * ny * nz;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(i % nx), l = (int)((i / nx) % ny), m = (int)(i / ((int64_t)nx * ny));
-        const int64_t dst = ((int64_t)k * ny + l) * nz + m;
-        const int64_t src = i + (int64_t)nx * ny;
-        aos[3 * dst] = s0[src];
-        aos[3 * dst + 1] = s1[src];
-        aos[3 * dst + 2] = s2[src];
+    __shared__ double tile[3][TT][TT + 1];  // [d][k][m]
+    const int k0 = blockIdx.x * TT, l = blockIdx.y, m0 = blockIdx.z * TT;
+    const int mt = min(TT, nz - m0), kt = min(TT, nx - k0);
+    const int tid = threadIdx.y * TT + threadIdx.x;
+    const double *src[3] = {s0, s1, s2};
+    const int kk = threadIdx.x;
+    for (int mm = threadIdx.y; mm < mt; mm += 8) {
+        if (kk < kt) {
+            const int64_t at = ((int64_t)(m0 + mm + 1) * ny + l) * nx + k0 + kk;
+#pragma unroll
+            for (int d = 0; d < 3; d++) tile[d][kk][mm] = src[d][at];
+        }
+    }
+    __syncthreads();
+    for (int k2 = 0; k2 < kt; k2++) {
+        const int64_t base = (((int64_t)(k0 + k2) * ny + l) * nz + m0) * 3;
+        for (int j = tid; j < 3 * mt; j += TT * 8) aos[base + j] = tile[j % 3][k2][j / 3];
     }
 }
 
@@ -175,7 +197,8 @@ int sg_setup(mm_handle *h) {
     g.nblocks_alloc = g.nblocks;
     MM_CUDA(cudaMalloc(&g.d_partials, sizeof(double) * (size_t)g.nblocks * kRedSlots));
     k_type_to_soa<<<grid_for(h, h->ncells, 256), 256, 0, h->stream>>>(h->d_cell_info, g.type, g.nx, g.ny, g.nzl);
-    k_halo_u8<<<grid_for(h, g.plane, 256), 256, 0, h->stream>>>(g.type, g.plane, g.nzl);
+    if (h->slab_count <= 1)  // slabs receive the neighbours' boundary types in mm_comm_init
+        k_halo_u8<<<grid_for(h, g.plane, 256), 256, 0, h->stream>>>(g.type, g.plane, g.nzl);
     MM_CUDA(cudaGetLastError());
     g.active = 1;
     return MM_OK;
@@ -227,6 +250,7 @@ int sg_halo(mm_handle *h, bool pos, bool vel, bool grad) {
     if (grad)
         for (int d = 0; d < 3; d++) ha.f[ha.nfields++] = g.g[g.cg][d];
     if (ha.nfields == 0) return MM_OK;
+    if (h->slab_count > 1) return comm_halo(h, ha.f, ha.nfields, ha.npos);  // planes travel between the slabs
     k_halo<<<grid_for(h, g.plane, 256), 256, 0, h->stream>>>(ha, g.plane, g.nzl, g.d_sc);
     h->launches++;
     return MM_OK;
@@ -239,21 +263,24 @@ int sg_halo_mass(mm_handle *h) {
     ha.npos = 0;
     ha.f[0] = g.m;
     ha.f[1] = g.minv;
+    if (h->slab_count > 1) return comm_halo(h, ha.f, 2, 0);
     k_halo<<<grid_for(h, g.plane, 256), 256, 0, h->stream>>>(ha, g.plane, g.nzl, g.d_sc);
     h->launches++;
     return MM_OK;
 }
 
+static dim3 transpose_grid(const SGrid &g) { return dim3((g.nx + TT - 1) / TT, g.ny, (g.nzl + TT - 1) / TT); }
+
 int sg_pos_from_aos(mm_handle *h, const double *d_aos) {
     SGrid &g = h->sg;
-    k_aos_to_soa<<<grid_for(h, h->nnodes, 256), 256, 0, h->stream>>>(d_aos, g.x[g.cx][0], g.x[g.cx][1], g.x[g.cx][2], g.nx, g.ny, g.nzl);
+    k_aos_to_soa<<<transpose_grid(g), dim3(TT, 8), 0, h->stream>>>(d_aos, g.x[g.cx][0], g.x[g.cx][1], g.x[g.cx][2], g.nx, g.ny, g.nzl);
     h->launches++;
     return sg_halo(h, true, false, false);
 }
 
 int sg_vel_from_aos(mm_handle *h, const double *d_aos) {
     SGrid &g = h->sg;
-    k_aos_to_soa<<<grid_for(h, h->nnodes, 256), 256, 0, h->stream>>>(d_aos, g.v[g.cv][0], g.v[g.cv][1], g.v[g.cv][2], g.nx, g.ny, g.nzl);
+    k_aos_to_soa<<<transpose_grid(g), dim3(TT, 8), 0, h->stream>>>(d_aos, g.v[g.cv][0], g.v[g.cv][1], g.v[g.cv][2], g.nx, g.ny, g.nzl);
     h->launches++;
     return sg_halo(h, false, true, false);
 }
@@ -268,7 +295,7 @@ int sg_mass_from_aos(mm_handle *h, const double *d_masses) {
 int sg_to_aos(mm_handle *h, int which, double *d_aos) {  // 0 pos, 1 vel, 2 gpos
     SGrid &g = h->sg;
     double **src = which == 0 ? g.x[g.cx] : which == 1 ? g.v[g.cv] : g.g[g.cg];
-    k_soa_to_aos<<<grid_for(h, h->nnodes, 256), 256, 0, h->stream>>>(src[0], src[1], src[2], d_aos, g.nx, g.ny, g.nzl);
+    k_soa_to_aos<<<transpose_grid(g), dim3(TT, 8), 0, h->stream>>>(src[0], src[1], src[2], d_aos, g.nx, g.ny, g.nzl);
     h->launches++;
     return MM_OK;
 }

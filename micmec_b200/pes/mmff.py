@@ -115,9 +115,12 @@ class ForcePartMechanical(ForcePart):
         least 4096 nodes), ``True`` / ``False`` force the choice; systems that do not qualify ignore it.
     """
 
-    def __init__(self, system, model=None, device=0, structured=None):
+    def __init__(self, system, model=None, device=0, structured=None, slab=None):
         ForcePart.__init__(self, "micmec", system)
         self.system = system
+        # slab = (rank, count, nnodes_global): `system` is one z-slab of a periodic grid spread over `count` GPUs
+        # (micmec_b200/slab.py); call init_comm() on every rank before the first compute
+        self.slab = slab
         self.model = model or os.environ.get("MICMEC_MODEL", "original")
         if self.model not in _lib.MODELS:
             raise ValueError("Unknown per-cell model %r (expected 'original' or 'default')." % (self.model,))
@@ -149,6 +152,8 @@ class ForcePartMechanical(ForcePart):
         shape = getattr(system, "structured_shape", None)
         if shape is not None and self.pbc and system.surrounding_nodes is None:
             desc.nx, desc.ny, desc.nz = (int(s) for s in shape)
+            if self.slab is not None:
+                desc.slab_rank, desc.slab_count, desc.nnodes_global = (int(v) for v in self.slab)
         else:
             sn = np.ascontiguousarray(system.surrounding_nodes, dtype=np.int64)
             sc = np.ascontiguousarray(system.surrounding_cells, dtype=np.int64)
@@ -171,6 +176,11 @@ class ForcePartMechanical(ForcePart):
         if handle is not None and handle.value:
             self._lib.mm_destroy(handle)
             self._handle = ctypes.c_void_p()
+
+    def init_comm(self, unique_id, nccl_path=None):
+        """Join the NCCL communicator of the slab decomposition (``unique_id``: 128 bytes from rank 0, see slab.py)."""
+        path = nccl_path.encode() if nccl_path else None
+        _lib.check(self._lib.mm_comm_init(self._handle, path, bytes(unique_id)))
 
     @property
     def handle(self):
