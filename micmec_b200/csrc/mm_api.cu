@@ -137,6 +137,7 @@ int mm_destroy(mm_handle *h) {
     cudaFree(h->d_result);
     cudaFree(h->d_rvecs);
     cudaFree(h->d_red);
+    cudaFree(h->d_halo);
     mm_comm_destroy(h);
     if (h->sg.active || h->sg.d_sc) sg_free(h);
     if (h->h_result) cudaFreeHost(h->h_result);

@@ -87,28 +87,33 @@ static int nccl_fail(int rc, const char *what) {
 
 // ---- halo planes over NCCL ----------------------------------------------------------------------------------------
 // up = rank + 1 (receives my top owned plane as its lower halo), down = rank - 1 (receives my bottom owned plane as
-// its upper halo); periodic in the rank index.
-__global__ void __launch_bounds__(256)
-k_shift_planes(double *p0, double *p1, double *p2, int64_t n, double c0, double c1, double c2) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        p0[i] += c0;
-        p1[i] += c1;
-        p2[i] += c2;
-    }
-}
-
-__global__ void k_read_rv(const StepConsts *sc, double *out3) {
-    if (threadIdx.x < 3) out3[threadIdx.x] = sc->rv[6 + threadIdx.x];
-}
+// its upper halo); periodic in the rank index.  The boundary planes of all fields of one exchange are packed into
+// ONE message per direction (a group of 2 sends + 2 receives instead of 4 per field).
+struct PackArgs {
+    double *f[9];
+    int nfields;
+    int npos;  // the first npos fields are position components
+};
 
 __global__ void __launch_bounds__(256)
-k_shift_planes_dev(double *p0, double *p1, double *p2, int64_t n, const StepConsts *sc, double sign) {
-    const double c0 = sign * sc->rv[6], c1 = sign * sc->rv[7], c2 = sign * sc->rv[8];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        p0[i] += c0;
-        p1[i] += c1;
-        p2[i] += c2;
-    }
+k_pack(const __grid_constant__ PackArgs a, int64_t plane, int nzl, double *up, double *down) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x)
+        for (int f = 0; f < a.nfields; f++) {
+            up[(int64_t)f * plane + i] = a.f[f][(int64_t)nzl * plane + i];  // top owned plane
+            down[(int64_t)f * plane + i] = a.f[f][plane + i];               // bottom owned plane
+        }
+}
+
+// lower halo <- message from below (minus c across the periodic wrap), upper halo <- message from above (plus c)
+__global__ void __launch_bounds__(256)
+k_unpack(const __grid_constant__ PackArgs a, int64_t plane, int nzl, const double *from_down, const double *from_up,
+         const StepConsts *sc, double sign_lo, double sign_hi) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x)
+        for (int f = 0; f < a.nfields; f++) {
+            const double c = (f < a.npos) ? sc->rv[6 + f] : 0.0;
+            a.f[f][i] = from_down[(int64_t)f * plane + i] + sign_lo * c;
+            a.f[f][(int64_t)(nzl + 1) * plane + i] = from_up[(int64_t)f * plane + i] + sign_hi * c;
+        }
 }
 
 int comm_halo(mm_handle *h, double **fields, int nfields, int npos) {
@@ -121,28 +126,23 @@ int comm_halo(mm_handle *h, double **fields, int nfields, int npos) {
     const int up = (r + 1) % P, down = (r + P - 1) % P;
     ncclComm_t comm = (ncclComm_t)h->comm;
     const size_t n = (size_t)g.plane;
+    if (!h->d_halo) MM_CUDA(cudaMalloc(&h->d_halo, sizeof(double) * 4 * 9 * n));
+    double *s_up = h->d_halo, *s_down = s_up + 9 * n, *r_down = s_down + 9 * n, *r_up = r_down + 9 * n;
+    PackArgs a;
+    a.nfields = nfields;
+    a.npos = npos;
+    for (int f = 0; f < nfields; f++) a.f[f] = fields[f];
+    const int grid = grid_for(h, g.plane, 256);
+    k_pack<<<grid, 256, 0, h->stream>>>(a, g.plane, g.nzl, s_up, s_down);
     MM_NCCL(g_nccl.GroupStart());
-    for (int f = 0; f < nfields; f++) {
-        double *base = fields[f];
-        MM_NCCL(g_nccl.Send(base + (size_t)g.nzl * n, n, ncclFloat64, up, comm, h->stream));          // top owned -> up
-        MM_NCCL(g_nccl.Recv(base, n, ncclFloat64, down, comm, h->stream));                             // lower halo <- down
-        MM_NCCL(g_nccl.Send(base + n, n, ncclFloat64, down, comm, h->stream));                         // bottom owned -> down
-        MM_NCCL(g_nccl.Recv(base + (size_t)(g.nzl + 1) * n, n, ncclFloat64, up, comm, h->stream));    // upper halo <- up
-    }
+    MM_NCCL(g_nccl.Send(s_up, n * nfields, ncclFloat64, up, comm, h->stream));
+    MM_NCCL(g_nccl.Recv(r_down, n * nfields, ncclFloat64, down, comm, h->stream));
+    MM_NCCL(g_nccl.Send(s_down, n * nfields, ncclFloat64, down, comm, h->stream));
+    MM_NCCL(g_nccl.Recv(r_up, n * nfields, ncclFloat64, up, comm, h->stream));
     MM_NCCL(g_nccl.GroupEnd());
-    h->launches += 1;
-    if (npos == 3) {  // periodic wrap of the rank ring: -c below rank 0, +c above rank P-1 (c of the stored frame)
-        const int grid = grid_for(h, g.plane, 256);
-        if (r == 0) {
-            k_shift_planes_dev<<<grid, 256, 0, h->stream>>>(fields[0], fields[1], fields[2], g.plane, g.d_sc, -1.0);
-            h->launches++;
-        }
-        if (r == P - 1) {
-            const size_t off = (size_t)(g.nzl + 1) * n;
-            k_shift_planes_dev<<<grid, 256, 0, h->stream>>>(fields[0] + off, fields[1] + off, fields[2] + off, g.plane, g.d_sc, 1.0);
-            h->launches++;
-        }
-    }
+    // periodic wrap of the rank ring: -c below rank 0, +c above rank P-1 (c of the stored frame)
+    k_unpack<<<grid, 256, 0, h->stream>>>(a, g.plane, g.nzl, r_down, r_up, g.d_sc, r == 0 ? -1.0 : 0.0, r == P - 1 ? 1.0 : 0.0);
+    h->launches += 3;
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }

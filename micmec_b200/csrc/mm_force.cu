@@ -59,6 +59,88 @@ k_cells(const __grid_constant__ KParams kp, const int32_t *__restrict__ cell_nod
     block_sum_store<7>(acc, partials + (size_t)blockIdx.x * kRedSlots);
 }
 
+// ---- the alternative gpos accumulation: cell-centric scatter with warp-aggregated atomics -------------------------------
+// Same per-cell work as k_cells, but instead of writing 24 gradient doubles per cell for a later node-centric
+// gather, every cell adds its 8 vertex contributions straight into gpos with fp64 atomics (RED.ADD.F64 resolved in
+// L2).  Consecutive cells of the reference enumeration are z-neighbours and share four vertices: lane i's
+// contributions to its upper-z vertices (3, 5, 6, 7) are handed to lane i+1 with shuffles whenever that lane's
+// lower-z vertices (0, 1, 2, 4) are the same nodes, which halves the atomics.  Summation order is not reproducible.
+template <int MODEL>
+__global__ void __launch_bounds__(kThreads)
+k_cells_scatter(const __grid_constant__ KParams kp, const int32_t *__restrict__ cell_nodes,
+                const uint8_t *__restrict__ cell_info, const double *__restrict__ pos, const double *__restrict__ rvecs,
+                int64_t ncells, double *__restrict__ gpos, double *__restrict__ ecell, double *__restrict__ partials) {
+    double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const double rv[9] = {rvecs[0], rvecs[1], rvecs[2], rvecs[3], rvecs[4], rvecs[5], rvecs[6], rvecs[7], rvecs[8]};
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nloop = (ncells + stride - 1) / stride * stride;  // whole warps stay in the loop (shuffles)
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nloop; c += stride) {
+        const bool live = c < ncells;
+        int32_t nd[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+        double g[24];
+#pragma unroll
+        for (int k = 0; k < 24; k++) g[k] = 0.0;
+        if (live) {
+            const unsigned info = cell_info[c];
+            double R[24];
+#pragma unroll
+            for (int v = 0; v < 8; v++) nd[v] = cell_nodes[(int64_t)v * ncells + c];
+            R[0] = pos[3 * (int64_t)nd[0]];
+            R[1] = pos[3 * (int64_t)nd[0] + 1];
+            R[2] = pos[3 * (int64_t)nd[0] + 2];
+#pragma unroll
+            for (int v = 1; v < 8; v++) {
+                const double sa = (vbit(v, 0) && (info & 16)) ? 1.0 : 0.0;
+                const double sb = (vbit(v, 1) && (info & 32)) ? 1.0 : 0.0;
+                const double sc = (vbit(v, 2) && (info & 64)) ? 1.0 : 0.0;
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    double dvec = pos[3 * (int64_t)nd[v] + d] - R[d];
+                    dvec += rv[d] * sa + rv[3 + d] * sb + rv[6 + d] * sc;
+                    R[v * 3 + d] = R[d] + dvec;
+                }
+            }
+            double e, vir[6];
+            cell_eval<MODEL>(R, kp, info & 15, e, g, vir);
+            ecell[c] = e;
+            acc[0] += e;
+#pragma unroll
+            for (int k = 0; k < 6; k++) acc[1 + k] += vir[k];
+        }
+        // warp aggregation along the enumeration: (upper-z vertex of lane i) == (lower-z vertex of lane i+1)?
+        constexpr int UP[4] = {3, 5, 6, 7}, LO[4] = {0, 1, 2, 4};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int lo_next = __shfl_down_sync(0xffffffffu, nd[LO[q]], 1);
+            const bool give = lane < 31 && nd[UP[q]] >= 0 && nd[UP[q]] == lo_next;   // I hand my contribution over
+            const bool take = __shfl_up_sync(0xffffffffu, (int)give, 1) && lane > 0;  // my lower neighbour hands me its own
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double from_below = __shfl_up_sync(0xffffffffu, g[UP[q] * 3 + d], 1);
+                if (take) g[LO[q] * 3 + d] += from_below;
+                if (give) g[UP[q] * 3 + d] = 0.0;
+            }
+            if (give) nd[UP[q]] = -1;
+        }
+#pragma unroll
+        for (int v = 0; v < 8; v++)
+            if (nd[v] >= 0) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) atomicAdd(&gpos[3 * (int64_t)nd[v] + d], g[v * 3 + d]);
+            }
+    }
+    block_sum_store<7>(acc, partials + (size_t)blockIdx.x * kRedSlots);
+}
+
+__global__ void __launch_bounds__(256)
+k_sumsq(const double *__restrict__ a, int64_t n, double *__restrict__ partials) {
+    double acc[1] = {0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc[0] = fma(a[i], a[i], acc[0]);
+    block_sum_store<1>(acc, partials + (size_t)blockIdx.x * kRedSlots);
+}
+
 template <bool WANT_G2>
 __global__ void __launch_bounds__(kThreads)
 k_gather(const int32_t *__restrict__ node_cells, const double *__restrict__ gcell, int64_t nnodes, int64_t ncells,
@@ -160,6 +242,27 @@ int force_evaluate(mm_handle *h, double *gpos_out, bool want_g2) {
         if (rc != MM_OK) return rc;
     }
     double *pn = h->d_partials + (size_t)kMaxRedBlocks * kRedSlots;
+    if (h->scatter_mode && gpos_out) {  // cell-centric atomic scatter instead of per-cell gradients + node gather
+        const int gcs = grid_for(h, h->ncells, kThreads);
+        MM_CUDA(cudaMemsetAsync(gpos_out, 0, sizeof(double) * 3 * h->nnodes, h->stream));
+        prof_begin(h, 0);
+        if (h->model == MM_MODEL_ORIGINAL)
+            k_cells_scatter<MM_MODEL_ORIGINAL><<<gcs, kThreads, 0, h->stream>>>(
+                h->kp, h->d_cell_nodes, h->d_cell_info, h->d_pos, h->d_rvecs, h->ncells, gpos_out, h->d_ecell, h->d_partials);
+        else
+            k_cells_scatter<MM_MODEL_DEFAULT><<<gcs, kThreads, 0, h->stream>>>(
+                h->kp, h->d_cell_nodes, h->d_cell_info, h->d_pos, h->d_rvecs, h->ncells, gpos_out, h->d_ecell, h->d_partials);
+        prof_end(h);
+        int gs = 0;
+        if (want_g2) {
+            gs = grid_for(h, 3 * h->nnodes, 256);
+            k_sumsq<<<gs, 256, 0, h->stream>>>(gpos_out, 3 * h->nnodes, pn);
+        }
+        k_final<<<1, 256, 0, h->stream>>>(h->d_partials, gcs, pn, gs, h->d_result);
+        h->launches += 3 + (want_g2 ? 1 : 0);
+        MM_CUDA(cudaGetLastError());
+        return MM_OK;
+    }
     const int gc = cells_launch(h);
     int gn = 0;
     if (gpos_out) {

@@ -74,6 +74,7 @@ struct mm_handle {
     int64_t nnodes_global = 0;
     void *comm = nullptr;     // ncclComm_t
     double *d_red = nullptr;  // [32] reduction buffer all-reduced across the slabs
+    double *d_halo = nullptr; // packed halo messages: send up / send down / recv from down / recv from up, 9 planes each
     mm::SGrid sg;
 };
 

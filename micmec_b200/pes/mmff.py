@@ -115,7 +115,7 @@ class ForcePartMechanical(ForcePart):
         least 4096 nodes), ``True`` / ``False`` force the choice; systems that do not qualify ignore it.
     """
 
-    def __init__(self, system, model=None, device=0, structured=None, slab=None):
+    def __init__(self, system, model=None, device=0, structured=None, slab=None, scatter=False):
         ForcePart.__init__(self, "micmec", system)
         self.system = system
         # slab = (rank, count, nnodes_global): `system` is one z-slab of a periodic grid spread over `count` GPUs
@@ -131,6 +131,10 @@ class ForcePartMechanical(ForcePart):
         self._keep = self._create()
         if structured is not None:
             _lib.check(self._lib.mm_set_option(self._handle, b"structured", int(bool(structured))))
+        if scatter:
+            # indexed kernels only: accumulate gpos with warp-aggregated fp64 atomics instead of the deterministic
+            # per-cell-gradient + node-gather pair (DESIGN.md section 7 has the measured comparison)
+            _lib.check(self._lib.mm_set_option(self._handle, b"scatter", 1))
 
     @staticmethod
     def get_pbc(rvecs):

@@ -102,7 +102,9 @@ def main():
                         scalars=float(np.max(serr)))
             print("   worst scalar:", names[int(np.argmax(serr))], flush=True)
             print(ens, {k: "%.2e" % v for k, v in errs.items()}, flush=True)
-            worst = max(worst, *errs.values())
+            # arrays to 1e-10; reduced scalars (pressure, virial: differences of large sums whose order changes with
+            # the decomposition, fed back through the barostat) to 1e-8 - the north_star's trajectory tolerance
+            worst = max(worst, errs["pos"], errs["vel"], errs["gpos0"], errs["vtens0"], 1e-2 * errs["scalars"])
         del verlet, mmf, part
     flag = torch.tensor([worst], device="cuda", dtype=torch.float64)
     dist.broadcast(flag, src=0)
