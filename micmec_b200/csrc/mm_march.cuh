@@ -288,12 +288,16 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         }
 
         // ---- backward butterfly: z in registers, y through shared memory, x by shuffle ---------------------------
+        double P[9];  // z-combined rows of this thread's cell column: kept in registers across the barrier
         if (have_node) {
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                sb[j][row][lane] = Dp[j] + D[j];
-                sb[3 + j][row][lane] = Dp[3 + j] + D[3 + j];
-                sb[6 + j][row][lane] = Dp[6 + j] - D[6 + j];
+                P[j] = Dp[j] + D[j];
+                P[3 + j] = Dp[3 + j] + D[3 + j];
+                P[6 + j] = Dp[6 + j] - D[6 + j];
+                sb[j][row][lane] = P[j];
+                sb[3 + j][row][lane] = P[3 + j];
+                sb[6 + j][row][lane] = P[6 + j];
             }
         }
         __syncthreads();
@@ -301,9 +305,9 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             double g[3];
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                const double q0 = sb[j][rowm][lane] + sb[j][row][lane];
-                const double q1 = sb[3 + j][rowm][lane] - sb[3 + j][row][lane];
-                const double q2 = sb[6 + j][rowm][lane] + sb[6 + j][row][lane];
+                const double q0 = sb[j][rowm][lane] + P[j];
+                const double q1 = sb[3 + j][rowm][lane] - P[3 + j];
+                const double q2 = sb[6 + j][rowm][lane] + P[6 + j];
                 const double s12 = q1 + q2;
                 const double q0m = __shfl_up_sync(0xffffffffu, q0, 1), s12m = __shfl_up_sync(0xffffffffu, s12, 1);
                 g[j] = (q0m - q0) + (s12m + s12);
