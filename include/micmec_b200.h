@@ -78,6 +78,11 @@ typedef struct {
      * reference order (id = (k*ny + l)*nz + m_local).  Needs mm_comm_init before the first compute. */
     int32_t slab_rank, slab_count;
     int64_t nnodes_global;
+    /* Batch of independent replicas (no communication, no reference counterpart): with nreplicas > 1 the arrays above
+     * describe nreplicas systems of nnodes / nreplicas nodes and ncells / nreplicas cells each, concatenated (index
+     * arrays already offset).  Every replica has its own domain vectors (mm_set_rvecs_batch); mm_compute returns the
+     * summed energy / virial and mm_get_replica_results the per-replica values. */
+    int64_t nreplicas;
 } mm_desc;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
@@ -112,6 +117,10 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value);
 /* with "profile" on: launches timed since the last call and their summed device time (ms), separately for
  * [0] force-only kernels and [1] fused kick-drift-force-kick kernels; synchronises the stream and resets the counters */
 int mm_profile(mm_handle *h, int64_t nlaunch[2], double total_ms[2]);
+
+/* ---- replica batches ---------------------------------------------------------------------------------------- */
+int mm_set_rvecs_batch(mm_handle *h, const double *rvecs_host /* [nreplicas][3][3] */);
+int mm_get_replica_results(mm_handle *h, double *energies_host /* [nreplicas] */, double *vtens_host /* [nreplicas][3][3] or NULL */);
 
 /* ---- multi-GPU (no reference counterpart: the reference is single-process) ---------------------------------- */
 /* NCCL bootstrap: rank 0 creates a 128-byte unique id, the host side broadcasts it (torch.distributed), every rank

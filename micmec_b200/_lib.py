@@ -24,7 +24,7 @@ S_VTENS, S_PTENS, S_NFORCE, S_COUNT = 16, 25, 34, 40
 EXPORTS = [
     "mm_create", "mm_destroy", "mm_last_error", "mm_version", "mm_device_ok", "mm_set_pos", "mm_set_rvecs",
     "mm_compute", "mm_get_cell_cache", "mm_launch_count", "mm_device_ptr", "mm_set_stream", "mm_synchronize",
-    "mm_set_option", "mm_profile", "mm_comm_unique_id", "mm_comm_init", "mm_comm_destroy", "mm_domain", "mm_md_create", "mm_md_destroy", "mm_md_init", "mm_md_set_state", "mm_md_run", "mm_md_get_state",
+    "mm_set_option", "mm_profile", "mm_set_rvecs_batch", "mm_get_replica_results", "mm_comm_unique_id", "mm_comm_init", "mm_comm_destroy", "mm_domain", "mm_md_create", "mm_md_destroy", "mm_md_init", "mm_md_set_state", "mm_md_run", "mm_md_get_state",
     "mm_md_scalars",
 ]
 
@@ -52,6 +52,7 @@ class Desc(ctypes.Structure):
         ("slab_rank", ctypes.c_int32),
         ("slab_count", ctypes.c_int32),
         ("nnodes_global", ctypes.c_int64),
+        ("nreplicas", ctypes.c_int64),
     ]
 
 
@@ -103,6 +104,8 @@ def load():
     lib.mm_synchronize.argtypes = [vp]
     lib.mm_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.mm_profile.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(dbl)]  # int64[2], double[2]
+    lib.mm_set_rvecs_batch.argtypes = [vp, vp]
+    lib.mm_get_replica_results.argtypes = [vp, vp, vp]
     lib.mm_comm_unique_id.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
     lib.mm_comm_init.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p]
     lib.mm_comm_destroy.argtypes = [vp]

@@ -138,6 +138,9 @@ int mm_destroy(mm_handle *h) {
     cudaFree(h->d_rvecs);
     cudaFree(h->d_red);
     cudaFree(h->d_halo);
+    cudaFree(h->d_rvecs_batch);
+    cudaFree(h->d_vcell);
+    cudaFree(h->d_rep);
     mm_comm_destroy(h);
     if (h->sg.active || h->sg.d_sc) sg_free(h);
     if (h->h_result) cudaFreeHost(h->h_result);
@@ -187,6 +190,11 @@ int mm_create(const mm_desc *desc, mm_handle **out) {
     h->slab_count = desc->slab_count > 1 ? desc->slab_count : 1;
     h->slab_rank = desc->slab_count > 1 ? desc->slab_rank : 0;
     h->nnodes_global = desc->nnodes_global > 0 ? desc->nnodes_global : desc->nnodes * h->slab_count;
+    h->nreplicas = desc->nreplicas > 1 ? desc->nreplicas : 1;
+    if (h->nreplicas > 1 && (structured || desc->nnodes % h->nreplicas != 0 || desc->ncells % h->nreplicas != 0)) {
+        delete h;
+        return invalid("mm_create: a replica batch needs indexed topology and equal-sized replicas");
+    }
 
     // ---- parameters (mmff.py:219-231) -----------------------------------------------------------------------
     memset(&h->kp, 0, sizeof(h->kp));
@@ -302,6 +310,12 @@ int mm_create(const mm_desc *desc, mm_handle **out) {
     MM_TRY(cudaMalloc(&h->d_partials, sizeof(double) * 2 * kMaxRedBlocks * kRedSlots));
     MM_TRY(cudaMalloc(&h->d_result, sizeof(ForceResult)));
     MM_TRY(cudaMalloc(&h->d_rvecs, sizeof(double) * 9));
+    if (h->nreplicas > 1) {
+        MM_TRY(cudaMalloc(&h->d_rvecs_batch, sizeof(double) * 9 * h->nreplicas));
+        MM_TRY(cudaMalloc(&h->d_vcell, sizeof(double) * 6 * nc));
+        MM_TRY(cudaMalloc(&h->d_rep, sizeof(double) * 8 * h->nreplicas));
+        MM_TRY(cudaMemsetAsync(h->d_rvecs_batch, 0, sizeof(double) * 9 * h->nreplicas, h->stream));
+    }
     MM_TRY(cudaHostAlloc(&h->h_result, sizeof(ForceResult), cudaHostAllocDefault));
     MM_TRY(cudaMemsetAsync(h->d_rvecs, 0, sizeof(double) * 9, h->stream));
     MM_TRY(cudaMemsetAsync(h->d_gpos, 0, sizeof(double) * 3 * nn, h->stream));
@@ -469,6 +483,34 @@ int mm_compute(mm_handle *h, double *energy_host, double *gpos, int where, doubl
                 set_error("Some ``vtens`` element(s) is/are not-a-number (``nan``).");
                 return MM_ERR_NAN;
             }
+    return MM_OK;
+}
+
+int mm_set_rvecs_batch(mm_handle *h, const double *rvecs) {
+    if (!h || !rvecs) return invalid("mm_set_rvecs_batch: null argument");
+    if (h->nreplicas <= 1) return invalid("mm_set_rvecs_batch: the handle is not a replica batch");
+    MM_CUDA(cudaSetDevice(h->device));
+    MM_CUDA(cudaMemcpyAsync(h->d_rvecs_batch, rvecs, sizeof(double) * 9 * h->nreplicas, cudaMemcpyHostToDevice, h->stream));
+    MM_CUDA(cudaStreamSynchronize(h->stream));  // the source is the caller's pageable array
+    return MM_OK;
+}
+
+int mm_get_replica_results(mm_handle *h, double *energies, double *vtens) {
+    if (!h || !energies) return invalid("mm_get_replica_results: null argument");
+    if (h->nreplicas <= 1) return invalid("mm_get_replica_results: the handle is not a replica batch");
+    MM_CUDA(cudaSetDevice(h->device));
+    std::vector<double> tmp((size_t)h->nreplicas * 8);
+    MM_CUDA(cudaMemcpyAsync(tmp.data(), h->d_rep, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+    MM_CUDA(cudaStreamSynchronize(h->stream));
+    for (int64_t r = 0; r < h->nreplicas; r++) {
+        const double *s = tmp.data() + r * 8;
+        energies[r] = s[0];
+        if (vtens) {
+            double *v = vtens + r * 9;
+            v[0] = s[1]; v[4] = s[2]; v[8] = s[3];
+            v[5] = v[7] = s[4]; v[2] = v[6] = s[5]; v[1] = v[3] = s[6];
+        }
+    }
     return MM_OK;
 }
 

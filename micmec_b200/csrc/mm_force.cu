@@ -17,16 +17,28 @@ namespace mm {
 
 constexpr int kThreads = 128;
 
-template <int MODEL>
+// BATCH: the system is a batch of independent replicas of `cpr` cells each; replica r has its own domain vectors
+// rvecs[r][9] and its per-cell virial is kept (vcell, SoA [6][ncells]) for the per-replica reduction.
+template <int MODEL, bool BATCH>
 __global__ void __launch_bounds__(kThreads)
 k_cells(const __grid_constant__ KParams kp, const int32_t *__restrict__ cell_nodes,
         const uint8_t *__restrict__ cell_info, const double *__restrict__ pos, const double *__restrict__ rvecs,
-        int64_t ncells, double *__restrict__ gcell, double *__restrict__ ecell, double *__restrict__ partials) {
+        int64_t ncells, double *__restrict__ gcell, double *__restrict__ ecell, double *__restrict__ partials,
+        int64_t cpr, double *__restrict__ vcell) {
     double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    const double rv[9] = {rvecs[0], rvecs[1], rvecs[2], rvecs[3], rvecs[4], rvecs[5], rvecs[6], rvecs[7], rvecs[8]};
+    double rv[9];
+    if (!BATCH) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) rv[i] = rvecs[i];
+    }
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (int64_t)gridDim.x * blockDim.x) {
         const unsigned info = cell_info[c];
         const int type = info & 15;
+        if (BATCH) {
+            const double *rr = rvecs + 9 * (c / cpr);
+#pragma unroll
+            for (int i = 0; i < 9; i++) rv[i] = rr[i];
+        }
         double R[24];
         const int64_t n0 = cell_nodes[c];
         const double r0x = pos[3 * n0], r0y = pos[3 * n0 + 1], r0z = pos[3 * n0 + 2];
@@ -55,8 +67,28 @@ k_cells(const __grid_constant__ KParams kp, const int32_t *__restrict__ cell_nod
         acc[0] += e;
 #pragma unroll
         for (int k = 0; k < 6; k++) acc[1 + k] += vir[k];
+        if (BATCH) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) vcell[(int64_t)k * ncells + c] = vir[k];
+        }
     }
     block_sum_store<7>(acc, partials + (size_t)blockIdx.x * kRedSlots);
+}
+
+// per-replica energy and virial: one thread per replica sums its cells in index order (deterministic)
+__global__ void __launch_bounds__(128)
+k_replica_reduce(const double *__restrict__ ecell, const double *__restrict__ vcell, int64_t ncells, int64_t cpr,
+                 int64_t nrep, double *__restrict__ out /* [nrep][8] */) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrep; r += (int64_t)gridDim.x * blockDim.x) {
+        double s[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int64_t c = r * cpr; c < (r + 1) * cpr; c++) {
+            s[0] += ecell[c];
+#pragma unroll
+            for (int k = 0; k < 6; k++) s[1 + k] += vcell[(int64_t)k * ncells + c];
+        }
+#pragma unroll
+        for (int k = 0; k < 7; k++) out[r * 8 + k] = s[k];
+    }
 }
 
 // ---- the alternative gpos accumulation: cell-centric scatter with warp-aggregated atomics -------------------------------
@@ -206,17 +238,28 @@ void prof_end(mm_handle *h) {
 
 int cells_launch(mm_handle *h) {
     const int gc = grid_for(h, h->ncells, kThreads);
+    const bool batch = h->nreplicas > 1;
+    const double *rv = batch ? h->d_rvecs_batch : h->d_rvecs;
+    const int64_t cpr = batch ? h->ncells / h->nreplicas : h->ncells;
     prof_begin(h, 0);
-    if (h->model == MM_MODEL_ORIGINAL)
-        k_cells<MM_MODEL_ORIGINAL><<<gc, kThreads, 0, h->stream>>>(h->kp, h->d_cell_nodes, h->d_cell_info, h->d_pos,
-                                                                   h->d_rvecs, h->ncells, h->d_gcell, h->d_ecell,
-                                                                   h->d_partials);
-    else
-        k_cells<MM_MODEL_DEFAULT><<<gc, kThreads, 0, h->stream>>>(h->kp, h->d_cell_nodes, h->d_cell_info, h->d_pos,
-                                                                  h->d_rvecs, h->ncells, h->d_gcell, h->d_ecell,
-                                                                  h->d_partials);
+#define MM_LAUNCH_CELLS(MODEL, BATCH)                                                                                  \
+    k_cells<MODEL, BATCH><<<gc, kThreads, 0, h->stream>>>(h->kp, h->d_cell_nodes, h->d_cell_info, h->d_pos, rv, h->ncells, \
+                                                          h->d_gcell, h->d_ecell, h->d_partials, cpr, h->d_vcell)
+    if (h->model == MM_MODEL_ORIGINAL) {
+        if (batch) MM_LAUNCH_CELLS(MM_MODEL_ORIGINAL, true);
+        else MM_LAUNCH_CELLS(MM_MODEL_ORIGINAL, false);
+    } else {
+        if (batch) MM_LAUNCH_CELLS(MM_MODEL_DEFAULT, true);
+        else MM_LAUNCH_CELLS(MM_MODEL_DEFAULT, false);
+    }
+#undef MM_LAUNCH_CELLS
     prof_end(h);
     h->launches++;
+    if (batch) {
+        k_replica_reduce<<<grid_for(h, h->nreplicas, 128), 128, 0, h->stream>>>(h->d_ecell, h->d_vcell, h->ncells, cpr,
+                                                                                 h->nreplicas, h->d_rep);
+        h->launches++;
+    }
     return gc;
 }
 

@@ -74,6 +74,11 @@ struct mm_handle {
     int64_t nnodes_global = 0;
     void *comm = nullptr;     // ncclComm_t
     double *d_red = nullptr;  // [32] reduction buffer all-reduced across the slabs
+    // batch of independent replicas (config 5): per-replica domain vectors, per-cell virial, per-replica results
+    int64_t nreplicas = 1;
+    double *d_rvecs_batch = nullptr;  // [nreplicas][9]
+    double *d_vcell = nullptr;        // [6][ncells]
+    double *d_rep = nullptr;          // [nreplicas][8]: energy, virial(6), pad
     double *d_halo = nullptr; // packed halo messages: send up / send down / recv from down / recv from up, 9 planes each
     mm::SGrid sg;
 };

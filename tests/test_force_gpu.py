@@ -291,3 +291,30 @@ def test_atomic_scatter_matches_gather(model):
             out.append((mmf.compute(g, v), g, v))
         assert out[0][0] == out[1][0] and np.array_equal(out[0][2], out[1][2])  # energy / virial: same kernel code
         assert gio.rel_rms(out[1][1], out[0][1]) <= 1e-13
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_replica_batch_matches_per_system_oracle(model):
+    """Config 5 in small: defect configurations x perturbations x strained cells evaluated as ONE batch."""
+    from micmec_b200.replicas import ReplicaBatch
+
+    names = ["3x3x3_conf0", "3x3x3_conf3", "3x3x3_conf9"]
+    base = [make_system(gio.load("force_" + n)) for n in names]
+    rng = np.random.default_rng(21)
+    systems, pos, rvecs = [], [], []
+    for rep in range(12):
+        s = base[rep % 3]
+        strain = np.eye(3) + 0.01 * rng.standard_normal((3, 3))
+        systems.append(s)
+        pos.append((s.pos + 0.3 * rng.standard_normal(s.pos.shape)) @ strain)
+        rvecs.append(np.array(s.domain.rvecs) @ strain)
+    batch = ReplicaBatch(systems, model=model)
+    e, g, v = batch.compute(np.array(pos), np.array(rvecs))
+    assert e.shape == (12,) and g.shape == (12, 27, 3) and v.shape == (12, 3, 3)
+    for rep in range(12):
+        o = orc.Oracle(base[rep % 3], model=model)
+        eo, go, vo = o.compute(pos[rep], rvecs[rep], gpos=True, vtens=True)
+        _, gc, vc = o.deformation(pos[rep], rvecs[rep])
+        check_against(e[rep], g[rep], v[rep], eo, go, vo, gio.virial_noise(gc, vc))
+    e2, g2, v2 = batch.compute(np.array(pos), np.array(rvecs), gpos=False)
+    assert g2 is None and np.array_equal(e2, e) and np.array_equal(v2, v)
