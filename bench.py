@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tile-rows", type=int, default=0, help="tuning: warps per block of the marching kernel (8/12/16)")
-    ap.add_argument("--ahg", type=int, default=-1, help="tuning: elasticity block via global loads (0/1)")
+    ap.add_argument("--psync", type=int, default=-1, help="tuning: pairwise named-barrier row handshakes in the marching kernel (0/1)")
     ap.add_argument("--generic", action="store_true", help="force the indexed-topology kernels (no structured path)")
     return ap.parse_args()
 
@@ -53,14 +53,14 @@ def parse_args():
 FORCE_EVALS = {"nve": 1, "nvt": 1, "npt": 3}
 
 
-def make_state(grid, seed=0, amp=0.1):
+def make_state(grid, seed=0, amp=0.1, explicit=False):
     """Synthetic G^3 fcu grid: rest lattice + `amp` bohr Gaussian displacement, Maxwell-Boltzmann velocities at
     300 K with the centre-of-mass motion removed (same recipe as sampling/utils.get_random_vel, seeded)."""
     from micmec_b200.system import System
     from micmec_b200.celltypes import TYPE_FCU
     from micmec_b200.units import boltzmann
 
-    system = System.periodic_grid((grid,) * 3, TYPE_FCU, explicit=grid <= 64)
+    system = System.periodic_grid((grid,) * 3, TYPE_FCU, explicit=explicit)
     rng = np.random.default_rng(seed)
     system.pos += amp * rng.standard_normal(system.pos.shape)
     vel = rng.standard_normal(system.pos.shape) * np.sqrt(boltzmann * 300.0 / system.masses)[:, None]
@@ -127,7 +127,7 @@ def cpu_oracle_rate(grid, ensemble, model, steps, nthreads):
     reported CPU baseline, never the product path)."""
     from oracle import oracle as orc
 
-    system, vel = make_state(grid)
+    system, vel = make_state(grid, explicit=True)
     p = md_params(ensemble)
     o = orc.Oracle(system, model=model, nthreads=nthreads)
     thermo = dict(temp=p["temp"], timecon=p["timecon_thermo"], chain_vel0=p["chain_vel0"], chain_pos0=np.zeros(3)) if p["thermo"] else None
@@ -216,8 +216,8 @@ def main():
         part = ForcePartMechanical(system, model=args.model, device=local_rank, slab=layout.slab_arg())
     if args.tile_rows:
         _lib.check(lib.mm_set_option(part.handle, b"tile_rows", args.tile_rows))
-    if args.ahg >= 0:
-        _lib.check(lib.mm_set_option(part.handle, b"ahg", args.ahg))
+    if args.psync >= 0:
+        _lib.check(lib.mm_set_option(part.handle, b"psync", args.psync))
     mmf = MicMecForceField(system, [part])
     stream = torch.cuda.Stream(device=local_rank)
     _lib.check(lib.mm_set_stream(part.handle, ctypes.c_void_p(stream.cuda_stream)))

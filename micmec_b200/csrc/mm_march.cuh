@@ -12,116 +12,112 @@ namespace mm {
 constexpr int TX = 32;  // lanes along x: one warp per tile row
 
 // ---------------------------------------------------------------------------------------------------------------
-// one state of one cell from Hs = 4 H (rows = summed edge vectors); constants pre-scaled (SState)
-// Ahg: the state's folded elasticity (36 doubles) in GLOBAL memory.  FP64 instructions on sm_100 take constants only
-// from (uniform) registers; 56 constant doubles per state overflow the uniform register file and ptxas then spills
-// uniform registers through vector registers inside the plane loop (~85 instructions per plane).  Reading the 6x6
-// block with explicit, non-hoistable 16-byte read-only loads (L1 broadcast) keeps it out of the register files.
-__device__ __forceinline__ void ld2(const double *p, double &a, double &b) {
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+// One state of one cell from Hs = 4 H (rows = summed edge vectors).  The reference chain (nanocell_original.py:69-132)
+//     G = h0^-1 H,  eps = 1/2 (G G^T - I),  s = sym(C:eps),  E = 1/2 V0 eps:s,  D = V0 h0^-T s G
+// is evaluated through the metric of the edge vectors, c = H H^T (6 unique entries), which removes h0^-1 from the
+// per-cell work:  G G^T - I = h0^-1 (c - c0) h0^-T with c0 = h0 h0^T, so with the two congruences folded into the
+// elasticity block on the host (fold_sparams),
+//     d  = Hs Hs^T - 16 c0                      (18 FMA; the rest value enters the FMA chain first, as -1 did before)
+//     Sq = Bq d                                 (36 FMA)    Bq = V0/512 K' A K,  Sq = V0/16 h0^-T s h0^-1
+//     E  = 1/4 d:Sq,   D' = D/4 = Sq Hs         (7 + 27)    vir = D'^T Hs  (18, includes V0)
+// 88 FP64 instructions per cell-state instead of 142, and a multi-state cell mixes the 6 entries of Sq, not D.
+__device__ __forceinline__ void smetric(const double Hs[9], double c[6]) {  // Voigt order 00 11 22 12 02 01
+    c[0] = fma(Hs[2], Hs[2], fma(Hs[1], Hs[1], Hs[0] * Hs[0]));
+    c[1] = fma(Hs[5], Hs[5], fma(Hs[4], Hs[4], Hs[3] * Hs[3]));
+    c[2] = fma(Hs[8], Hs[8], fma(Hs[7], Hs[7], Hs[6] * Hs[6]));
+    c[3] = fma(Hs[5], Hs[8], fma(Hs[4], Hs[7], Hs[3] * Hs[6]));
+    c[4] = fma(Hs[2], Hs[8], fma(Hs[1], Hs[7], Hs[0] * Hs[6]));
+    c[5] = fma(Hs[2], Hs[5], fma(Hs[1], Hs[4], Hs[0] * Hs[3]));
 }
 
-template <bool AHG, bool WANT_VIR>
-__device__ __forceinline__ void sstate_eval(const double Hs[9], const SState &P, const double *__restrict__ Ahg, double &e,
-                                            double D[9], double vir[6]) {
-    double G[9];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-            G[i * 3 + j] = fma(P.hiq[i * 3 + 2], Hs[6 + j], fma(P.hiq[i * 3 + 1], Hs[3 + j], P.hiq[i * 3] * Hs[j]));
-    double u[6];  // u = G G^T - I = 2 eps
-    u[0] = fma(G[2], G[2], fma(G[1], G[1], fma(G[0], G[0], -1.0)));
-    u[1] = fma(G[5], G[5], fma(G[4], G[4], fma(G[3], G[3], -1.0)));
-    u[2] = fma(G[8], G[8], fma(G[7], G[7], fma(G[6], G[6], -1.0)));
-    u[3] = fma(G[5], G[8], fma(G[4], G[7], G[3] * G[6]));
-    u[4] = fma(G[2], G[8], fma(G[1], G[7], G[0] * G[6]));
-    u[5] = fma(G[2], G[5], fma(G[1], G[4], G[0] * G[3]));
-    double s[6];
+// d = c - c0 of one state -> Sq and the elastic energy (without efree)
+__device__ __forceinline__ void sstate_eval(const double d[6], const SState &P, double &e, double Sq[6]) {
 #pragma unroll
     for (int I = 0; I < 6; I++) {
-        if (AHG) {
-            double a0, a1, a2, a3, a4, a5;
-            ld2(Ahg + I * 6, a0, a1);
-            ld2(Ahg + I * 6 + 2, a2, a3);
-            ld2(Ahg + I * 6 + 4, a4, a5);
-            s[I] = fma(a5, u[5], fma(a4, u[4], fma(a3, u[3], fma(a2, u[2], fma(a1, u[1], a0 * u[0])))));
-        } else {
-            double acc = P.Ah[I * 6] * u[0];
-#pragma unroll
-            for (int J = 1; J < 6; J++) acc = fma(P.Ah[I * 6 + J], u[J], acc);
-            s[I] = acc;
-        }
+        // two chains of three: halves the dependent-FMA depth of the longest chain in the plane loop
+        const double lo = fma(P.Bq[I * 6 + 2], d[2], fma(P.Bq[I * 6 + 1], d[1], P.Bq[I * 6] * d[0]));
+        Sq[I] = fma(P.Bq[I * 6 + 5], d[5], fma(P.Bq[I * 6 + 4], d[4], fma(P.Bq[I * 6 + 3], d[3], lo)));
     }
-    const double dens = fma(2.0, fma(u[5], s[5], fma(u[4], s[4], u[3] * s[3])), fma(u[2], s[2], fma(u[1], s[1], u[0] * s[0])));
-    e = P.v0q * dens;
-    double T[9];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        T[j] = fma(s[4], G[6 + j], fma(s[5], G[3 + j], s[0] * G[j]));
-        T[3 + j] = fma(s[3], G[6 + j], fma(s[1], G[3 + j], s[5] * G[j]));
-        T[6 + j] = fma(s[2], G[6 + j], fma(s[3], G[3 + j], s[4] * G[j]));
-    }
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-            D[i * 3 + j] = fma(P.hitv[i * 3 + 2], T[6 + j], fma(P.hitv[i * 3 + 1], T[3 + j], P.hitv[i * 3] * T[j]));
-    if (!WANT_VIR) return;
-    // G^T T (symmetric); the V0 factor is applied by the caller
-    vir[0] = fma(G[6], T[6], fma(G[3], T[3], G[0] * T[0]));
-    vir[1] = fma(G[7], T[7], fma(G[4], T[4], G[1] * T[1]));
-    vir[2] = fma(G[8], T[8], fma(G[5], T[5], G[2] * T[2]));
-    vir[3] = fma(G[7], T[8], fma(G[4], T[5], G[1] * T[2]));
-    vir[4] = fma(G[6], T[8], fma(G[3], T[5], G[0] * T[2]));
-    vir[5] = fma(G[6], T[7], fma(G[3], T[4], G[0] * T[1]));
+    const double dens = fma(2.0, fma(d[5], Sq[5], fma(d[4], Sq[4], d[3] * Sq[3])), fma(d[2], Sq[2], fma(d[1], Sq[1], d[0] * Sq[0])));
+    e = 0.25 * dens;
 }
 
-// all states of a cell, Boltzmann-mixed (mmff.py:377-398); the mixing is linear in the gradient, hence in D.
-// SINGLE (one type, one state): vir is returned WITHOUT the V0 factor (applied once per block by the caller).
-template <bool SINGLE, bool AHG, bool WANT_VIR>
-__device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp, const SParams *__restrict__ kpg, int type,
-                                           double &e, double D[9], double vir[6]) {
+// named barriers (PTX bar.arrive / bar.sync with a thread count): the producer-consumer handshake between two warps
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_wait(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// all states of a cell, Boltzmann-mixed (mmff.py:377-398); the mixing is linear in the gradient, hence in Sq.
+template <bool SINGLE, bool WANT_VIR>
+__device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp, int type, double &e, double D[9],
+                                           double vir[6]) {
+    double Sq[6];
     if (SINGLE) {
-        sstate_eval<AHG, WANT_VIR>(Hs, kp.st[0], kpg->st[0].Ah, e, D, vir);
-        e += kp.st[0].efree;
-        return;
-    }
-    const int ns = kp.nstates[type], off = kp.offset[type];
-    sstate_eval<AHG, true>(Hs, kp.st[off], kpg->st[off].Ah, e, D, vir);
-    e += kp.st[off].efree;
+        const SState &P = kp.st[0];
+        double d[6];
+        d[0] = fma(Hs[2], Hs[2], fma(Hs[1], Hs[1], fma(Hs[0], Hs[0], -P.c0[0])));
+        d[1] = fma(Hs[5], Hs[5], fma(Hs[4], Hs[4], fma(Hs[3], Hs[3], -P.c0[1])));
+        d[2] = fma(Hs[8], Hs[8], fma(Hs[7], Hs[7], fma(Hs[6], Hs[6], -P.c0[2])));
+        d[3] = fma(Hs[5], Hs[8], fma(Hs[4], Hs[7], fma(Hs[3], Hs[6], -P.c0[3])));
+        d[4] = fma(Hs[2], Hs[8], fma(Hs[1], Hs[7], fma(Hs[0], Hs[6], -P.c0[4])));
+        d[5] = fma(Hs[2], Hs[5], fma(Hs[1], Hs[4], fma(Hs[0], Hs[3], -P.c0[5])));
+        sstate_eval(d, P, e, Sq);
+        e += P.efree;
+    } else {
+        const int ns = kp.nstates[type], off = kp.offset[type];
+        double c[6], d[6];
+        smetric(Hs, c);
 #pragma unroll
-    for (int k = 0; k < 6; k++) vir[k] *= kp.st[off].v0;
-    if (ns == 1) return;
-    const double kT = kp.kT[type];
-    double emin = e, wsum = 1.0;
+        for (int k = 0; k < 6; k++) d[k] = c[k] - kp.st[off].c0[k];
+        sstate_eval(d, kp.st[off], e, Sq);
+        e += kp.st[off].efree;
+        if (ns > 1) {
+            const double kT = kp.kT[type];
+            double emin = e, wsum = 1.0;
 #pragma unroll 1
-    for (int s = 1; s < ns; s++) {
-        double es, Ds[9], vs[6];
-        sstate_eval<AHG, true>(Hs, kp.st[off + s], kpg->st[off + s].Ah, es, Ds, vs);
-        es += kp.st[off + s].efree;
-        double fo, fn;  // factors for the old accumulation and for the new state
-        if (es < emin) {
-            fo = exp(-(emin - es) / kT);
-            fn = 1.0;
-            emin = es;
-        } else {
-            fo = 1.0;
-            fn = exp(-(es - emin) / kT);
+            for (int s = 1; s < ns; s++) {
+                double es, Ss[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) d[k] = c[k] - kp.st[off + s].c0[k];
+                sstate_eval(d, kp.st[off + s], es, Ss);
+                es += kp.st[off + s].efree;
+                double fo, fn;  // factors for the old accumulation and for the new state
+                if (es < emin) {
+                    fo = exp(-(emin - es) / kT);
+                    fn = 1.0;
+                    emin = es;
+                } else {
+                    fo = 1.0;
+                    fn = exp(-(es - emin) / kT);
+                }
+                wsum = fma(wsum, fo, fn);
+#pragma unroll
+                for (int k = 0; k < 6; k++) Sq[k] = fma(Sq[k], fo, fn * Ss[k]);
+            }
+            const double inv = 1.0 / wsum;
+#pragma unroll
+            for (int k = 0; k < 6; k++) Sq[k] *= inv;
+            e = emin - kT * log(wsum);
         }
-        wsum = fma(wsum, fo, fn);
-        const double fv = fn * kp.st[off + s].v0;
-#pragma unroll
-        for (int k = 0; k < 9; k++) D[k] = fma(D[k], fo, fn * Ds[k]);
-#pragma unroll
-        for (int k = 0; k < 6; k++) vir[k] = fma(vir[k], fo, fv * vs[k]);
     }
-    const double inv = 1.0 / wsum;
+    // D' = Sq Hs with Sq = [[0 5 4], [5 1 3], [4 3 2]]
 #pragma unroll
-    for (int k = 0; k < 9; k++) D[k] *= inv;
-#pragma unroll
-    for (int k = 0; k < 6; k++) vir[k] *= inv;
-    e = emin - kT * log(wsum);
+    for (int j = 0; j < 3; j++) {
+        D[j] = fma(Sq[4], Hs[6 + j], fma(Sq[5], Hs[3 + j], Sq[0] * Hs[j]));
+        D[3 + j] = fma(Sq[3], Hs[6 + j], fma(Sq[1], Hs[3 + j], Sq[5] * Hs[j]));
+        D[6 + j] = fma(Sq[2], Hs[6 + j], fma(Sq[3], Hs[3 + j], Sq[4] * Hs[j]));
+    }
+    if (!WANT_VIR) return;
+    // cell virial sum_v g_v (x) r_v = D^T H = D'^T Hs (mmff.py:320-323; symmetric because Sq is)
+    vir[0] = fma(D[6], Hs[6], fma(D[3], Hs[3], D[0] * Hs[0]));
+    vir[1] = fma(D[7], Hs[7], fma(D[4], Hs[4], D[1] * Hs[1]));
+    vir[2] = fma(D[8], Hs[8], fma(D[5], Hs[5], D[2] * Hs[2]));
+    vir[3] = fma(D[7], Hs[8], fma(D[4], Hs[5], D[1] * Hs[2]));
+    vir[4] = fma(D[6], Hs[8], fma(D[3], Hs[5], D[0] * Hs[2]));
+    vir[5] = fma(D[6], Hs[7], fma(D[3], Hs[4], D[0] * Hs[1]));
 }
 
 // Template parameters
@@ -130,9 +126,9 @@ __device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp
 //   ROT     FORCE only: 1 = positions are rotated on load (x_true = (x + shift) . Rpend); 2 = and written back
 //   VM      STEP only: pending velocity transform  0 none, 1 scalar (Mvel[0]), 2 full 3x3
 //   LEAN    no virial, kinetic-energy diagonal only (NVE / NVT steps whose pressure nobody looks at)
-//   AHG     elasticity block read from global memory inside the loop instead of uniform registers
+//   PSYNC   neighbouring rows synchronise pairwise through named barriers instead of two block-wide barriers per plane
 //   TY      tile rows (warps per block); the tile owns (TX-2) x (TY-2) node columns
-template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, bool AHG, int TY>
+template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, bool PSYNC, int TY>
 __global__ void __launch_bounds__(TX *TY, 1)
 k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a, const int write_g) {
     constexpr int OX = TX - 2, OY = TY - 2;
@@ -248,7 +244,12 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             sf[j][row][lane] = px[j];
             sf[3 + j][row][lane] = dx[j];
         }
-        __syncthreads();
+        if (PSYNC) {  // row r only needs row r+1: producer arrives, consumer waits (barrier ids 1 .. TY-1)
+            if (row > 0) bar_arrive(row, 2 * TX);
+            if (row + 1 < TY) bar_wait(row + 1, 2 * TX);
+        } else {
+            __syncthreads();
+        }
         double pxy[3], dxy[3], pyd[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
@@ -271,7 +272,7 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             }
             const int type = SINGLE ? 0 : (int)a.type[idx - plane];
             double e, vir[6];
-            scell_eval<SINGLE, AHG, !LEAN>(Hs, kp, a.spd, type, e, D, vir);
+            scell_eval<SINGLE, !LEAN>(Hs, kp, type, e, D, vir);
             if (own_xy && have_node) {  // the warm-up layer c0-1 belongs to the chunk below
                 acc[0] += e;
                 if (!LEAN) {
@@ -300,7 +301,13 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
                 sb[6 + j][row][lane] = P[6 + j];
             }
         }
-        __syncthreads();
+        if (PSYNC) {  // row r only needs row r-1 (barrier ids TY .. 2 TY - 2); these two handshakes per plane also order
+                      // the reuse of sf / sb between planes
+            if (row + 1 < TY) bar_arrive(TY + row, 2 * TX);
+            if (row > 0) bar_wait(TY + row - 1, 2 * TX);
+        } else {
+            __syncthreads();
+        }
         if (have_node) {
             double g[3];
 #pragma unroll
@@ -350,10 +357,6 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         }
     }
 
-    if (SINGLE && !LEAN) {  // the V0 factor of the virial is common to every cell of the block
-#pragma unroll
-        for (int q = 0; q < 6; q++) acc[1 + q] *= kp.st[0].v0;
-    }
     // block reduction: warp shuffles, then one warp over the per-warp sums
     __shared__ double red[TY][14];
 #pragma unroll

@@ -69,6 +69,8 @@ enum : unsigned {
     OP_TAKE_DELTA = 1u << 10,
     OP_SETUP = 1u << 11,
     OP_POS_WRITTEN = 1u << 12,
+    OP_NEXT_THERMO = 1u << 13,  // the NEXT step's thermostat "pre" call, merged into this step's last scalar launch
+    OP_NEXT_BARO_A = 1u << 14,  // the NEXT step's first barostat half, likewise
 };
 
 // ------------------------------------------------------------------------------------------- 3x3 helpers ----
@@ -87,6 +89,35 @@ __device__ void sym_expm(const double *a_in, double scale, double *out) {
     double a[3][3], q[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) a[i][j] = (i >= j) ? a_in[i * 3 + j] : a_in[j * 3 + i];
+    {
+        // In MD the argument X = scale * A is tiny (barostat velocity x half a time step ~ 1e-6): the power series
+        // reaches 1e-17 in a few terms of independent 3x3 products, whereas the Jacobi sweeps below are a serial chain
+        // of divisions and square roots (~10 us on one thread).  Same result to rounding; Jacobi remains for large X.
+        double X[9], nrm = 0.0;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                X[i * 3 + j] = scale * a[i][j];
+                nrm += X[i * 3 + j] * X[i * 3 + j];
+            }
+        if (nrm < 1e-4) {  // ||X||_F < 1e-2: 9 terms give < 1e-2^10 / 10! = 3e-27 relative truncation
+            double term[9], sum[9], t[9];
+            for (int i = 0; i < 9; i++) {
+                term[i] = X[i];
+                sum[i] = ((i % 4 == 0) ? 1.0 : 0.0) + X[i];
+            }
+            for (int k = 2; k <= 9; k++) {
+                mat_mul(term, X, t);
+                const double inv = 1.0 / (double)k;
+                for (int i = 0; i < 9; i++) {
+                    term[i] = t[i] * inv;
+                    sum[i] += term[i];
+                }
+            }
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) out[i * 3 + j] = 0.5 * (sum[i * 3 + j] + sum[j * 3 + i]);
+            return;
+        }
+    }
     for (int sweep = 0; sweep < 64; sweep++) {
         const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
         const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
@@ -369,6 +400,11 @@ __device__ void scalar_ops(MDState &s, double *rvecs_dev, StepConsts *sc, unsign
         s.counter++;
     }
     if (ops & OP_PROPS) properties(s, n3);
+    if (ops & OP_NEXT_THERMO) thermo_call(s);
+    if (ops & OP_NEXT_BARO_A) {
+        baro_a(s);
+        for (int i = 0; i < 9; i++) rvecs_dev[i] = s.rvecs[i];
+    }
     if (sc) {
         for (int i = 0; i < 9; i++) {
             sc->Rpend[i] = s.Rpend[i];
@@ -545,6 +581,13 @@ struct mm_md {
     double *d_pdelta = nullptr;  // partials of k_delta
     bool initialised = false;
     bool structured = false;  // state lives in the SoA planes of h->sg
+    // CUDA graphs of TWO consecutive lean steps (two, because the ping-pong buffers return to the same parity after
+    // two steps), one per buffer-parity state.  A 64^3 NVE step is 26 us of kernel time but 4 launches with
+    // multi-kilobyte parameter blocks; replaying a captured pair removes the per-launch host cost.
+    cudaGraphExec_t gexec[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int64_t glaunches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t steps_done = 0;
+    int use_graphs = 1;
 };
 
 namespace mm {
@@ -588,19 +631,22 @@ static int baro_force(mm_md *md, bool snapshot, int &nbc, int &nbn) {
 }
 
 // VerletIntegrator.propagate (verlet.py:140-166).  `full` additionally produces rmsd_delta for this step.
-static int md_step(mm_md *md, bool full) {
+// own_pre: launch this step's first scalar "pre" call (false when the previous step merged it into its last launch);
+// merge_next: append the NEXT step's first "pre" call to this step's last scalar launch (only between lean steps).
+static int md_step(mm_md *md, bool full, bool own_pre, bool merge_next) {
     mm_handle *h = md->h;
     const bool thermo = md->desc.has_thermo != 0, baro = md->desc.has_baro != 0;
     const int gn = grid_for(h, h->nnodes, kNodeThreads);
     int nbc = 0, nbn = 0;
     // ---- "pre" hooks: TBCombination.pre = barostat, then thermostat (npt.py:99-115) ----
     if (baro) {
-        scalar_launch(md, OP_BARO_A, 0, 0, 0);
+        if (own_pre) scalar_launch(md, OP_BARO_A, 0, 0, 0);
         baro_force(md, full, nbc, nbn);
         scalar_launch(md, OP_TAKE_FORCE | OP_BARO_B | (thermo ? OP_THERMO : 0u), nbc, nbn, 0);
     } else if (thermo) {
-        scalar_launch(md, OP_THERMO, 0, 0, 0);
+        if (own_pre) scalar_launch(md, OP_THERMO, 0, 0, 0);
     }
+    const unsigned next_op = !merge_next ? 0u : baro ? OP_NEXT_BARO_A : thermo ? OP_NEXT_THERMO : 0u;
     // ---- velocity Verlet (verlet.py:144-154) ----
     k_kick_drift<<<gn, kNodeThreads, 0, h->stream>>>(md->d_state, h->d_pos, md->d_vel, h->d_gpos, md->d_masses,
                                                      (full && !baro) ? md->d_posold : nullptr, h->nnodes);
@@ -619,11 +665,11 @@ static int md_step(mm_md *md, bool full) {
             h->launches++;
             ops |= OP_TAKE_DELTA;
         }
-        scalar_launch(md, ops | OP_ECONS | OP_ADVANCE | OP_PROPS, nbc, gn, nbd);
+        scalar_launch(md, ops | OP_ECONS | OP_ADVANCE | OP_PROPS | next_op, nbc, gn, nbd);
     } else {
         scalar_launch(md, ops | OP_BARO_A, nbc, gn, 0);
         baro_force(md, false, nbc, nbn);
-        ops = OP_TAKE_FORCE | OP_BARO_B | OP_ECONS | OP_ADVANCE | OP_PROPS;
+        ops = OP_TAKE_FORCE | OP_BARO_B | OP_ECONS | OP_ADVANCE | OP_PROPS | next_op;
         if (full) {
             nbd = grid_for(h, 3 * h->nnodes, kNodeThreads);
             k_delta<<<nbd, kNodeThreads, 0, h->stream>>>(h->d_pos, md->d_posold, 3 * h->nnodes, md->d_pdelta);
@@ -667,20 +713,21 @@ static void sg_export(mm_md *md, bool pos, bool vel, double *pos_dst) {
 
 // The same step on the structured-grid kernels (mm_structured.cu): one fused kick-drift-force-kick launch, plus one
 // force-only launch per barostat call.  Pending rotations / scalings are consumed by the kernels on load.
-static int md_step_structured(mm_md *md, bool full) {
+static int md_step_structured(mm_md *md, bool full, bool own_pre, bool merge_next) {
     mm_handle *h = md->h;
     const bool thermo = md->desc.has_thermo != 0, baro = md->desc.has_baro != 0;
     const int nb = h->sg.nblocks;
-    if (full) sg_export(md, true, false, md->d_posold);  // posold of verlet.py:158-161
+    const unsigned next_op = !merge_next ? 0u : baro ? OP_NEXT_BARO_A : thermo ? OP_NEXT_THERMO : 0u;
+    if (full) sg_export(md, true, false, md->d_posold);  // posold of verlet.py:158-161 (a full step always has own_pre)
     if (baro) {
-        scalar_launch(md, OP_BARO_A, 0, 0, 0);
+        if (own_pre) scalar_launch(md, OP_BARO_A, 0, 0, 0);
         // npt.py:683-707: rotate the positions (all pending rotations at once) and evaluate; the rotated positions are
         // written back so that the fused step below needs no rotation; the gradient is what its first kick uses
         sg_force(h, true, 2);
         scalar_launch(md, OP_POS_WRITTEN | OP_TAKE_FORCE | OP_BARO_B | (thermo ? OP_THERMO : 0u), nb, nb, 0);
         sg_halo(h, true, false, true);  // after OP_POS_WRITTEN: the halo shift uses the new stored frame
     } else if (thermo) {
-        scalar_launch(md, OP_THERMO, 0, 0, 0);
+        if (own_pre) scalar_launch(md, OP_THERMO, 0, 0, 0);
     }
     // without a barostat the gradient written here feeds the next step's first kick
     sg_step(h, !baro, baro ? 2 : (thermo ? 1 : 0), !full);
@@ -695,12 +742,12 @@ static int md_step_structured(mm_md *md, bool full) {
             h->launches++;
             ops |= OP_TAKE_DELTA;
         }
-        scalar_launch(md, ops | OP_ECONS | OP_ADVANCE | OP_PROPS, nb, nb, nbd);
+        scalar_launch(md, ops | OP_ECONS | OP_ADVANCE | OP_PROPS | next_op, nb, nb, nbd);
     } else {
         scalar_launch(md, ops | OP_BARO_A, nb, nb, 0);
         sg_halo(h, true, true, false);  // after OP_POS_WRITTEN: the halo shift must use the new stored frame
         sg_force(h, full, 1);           // npt.py:683-707 again; this rotation stays pending until the next step
-        ops = OP_TAKE_FORCE | OP_BARO_B | OP_ECONS | OP_ADVANCE | OP_PROPS;
+        ops = OP_TAKE_FORCE | OP_BARO_B | OP_ECONS | OP_ADVANCE | OP_PROPS | next_op;
         if (full) {
             sg_export(md, true, false, h->d_pos);
             nbd = grid_for(h, 3 * h->nnodes, kNodeThreads);
@@ -727,6 +774,8 @@ int mm_md_destroy(mm_md *md) {
     cudaFree(md->d_pkin);
     cudaFree(md->d_pdelta);
     if (md->h_state) cudaFreeHost(md->h_state);
+    for (int i = 0; i < 8; i++)
+        if (md->gexec[i]) cudaGraphExecDestroy(md->gexec[i]);
     delete md;
     return MM_OK;
 }
@@ -894,11 +943,58 @@ int mm_md_run(mm_md *md, int64_t nsteps) {
         set_error("mm_md_run: integrator not initialised");
         return MM_ERR_STATE;
     }
-    MM_CUDA(cudaSetDevice(md->h->device));
-    for (int64_t i = 0; i < nsteps; i++) {
-        if (md->structured) md_step_structured(md, i == nsteps - 1);
-        else md_step(md, i == nsteps - 1);
+    mm_handle *h = md->h;
+    MM_CUDA(cudaSetDevice(h->device));
+    auto one_step = [&](bool full, bool own_pre, bool merge_next) {
+        return md->structured ? md_step_structured(md, full, own_pre, merge_next) : md_step(md, full, own_pre, merge_next);
+    };
+    // Step roles inside one call: L0 (own "pre" launch), middle lean steps (their "pre" was merged into the previous
+    // step's last scalar launch and they merge the next one's), the last lean step (does not merge: the final step takes
+    // its posold snapshot first), and the final FULL step (own "pre"; also produces rmsd_delta / gpos).
+    const int64_t lean = nsteps > 0 ? nsteps - 1 : 0;
+    // the first steps after initialisation run directly (lazy allocations happen there), as do profiled runs
+    const bool graphs = md->use_graphs && !h->profile && md->steps_done >= 2;
+    int64_t i = 0;
+    if (lean >= 1) {
+        one_step(false, true, lean >= 2);
+        i = 1;
     }
+    while (i + 1 < lean) {  // middle steps i .. lean-2
+        const int64_t left = lean - 1 - i;
+        if (!graphs || left < 2) {
+            one_step(false, false, true);
+            i++;
+            continue;
+        }
+        const int key = md->structured ? (h->sg.cx | (h->sg.cv << 1) | (h->sg.cg << 2)) : 0;
+        if (!md->gexec[key]) {  // capture two middle steps from the current buffer parity
+            cudaGraph_t graph = nullptr;
+            const int64_t before = h->launches;
+            MM_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = one_step(false, false, true);
+            if (rc == MM_OK) rc = one_step(false, false, true);
+            const cudaError_t err = cudaStreamEndCapture(h->stream, &graph);
+            md->glaunches[key] = h->launches - before;
+            h->launches = before;
+            if (rc != MM_OK || err != cudaSuccess || !graph) {
+                cudaGetLastError();
+                if (graph) cudaGraphDestroy(graph);
+                md->use_graphs = 0;  // fall back to direct launches for good
+                set_error("CUDA graph capture of the MD step failed");
+                return rc != MM_OK ? rc : MM_ERR_CUDA;
+            }
+            const cudaError_t ierr = cudaGraphInstantiate(&md->gexec[key], graph, 0);
+            cudaGraphDestroy(graph);
+            if (ierr != cudaSuccess) return cuda_fail(ierr, "cudaGraphInstantiate");
+            // capturing does not execute; the buffer-parity flags were flipped twice by the captured calls = unchanged
+        }
+        MM_CUDA(cudaGraphLaunch(md->gexec[key], h->stream));
+        h->launches += md->glaunches[key];
+        i += 2;
+    }
+    if (lean >= 2) one_step(false, false, false);  // last lean step
+    if (nsteps > 0) one_step(true, true, false);
+    md->steps_done += nsteps;
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }

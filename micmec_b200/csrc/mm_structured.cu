@@ -134,16 +134,61 @@ static void fold_sparams(const KParams &kp, SParams &sp) {
         sp.offset[t] = kp.offset[t];
         sp.kT[t] = kp.kT[t];
     }
+    static const int vi[6] = {0, 1, 2, 1, 0, 0}, vj[6] = {0, 1, 2, 2, 2, 1};
     for (int s = 0; s < MM_MAX_STATES; s++) {
         const StateP &P = kp.st[s];
         SState &S = sp.st[s];
-        for (int i = 0; i < 9; i++) S.hiq[i] = 0.25 * P.hi[i];
-        for (int i = 0; i < 36; i++) S.Ah[i] = 0.5 * P.A[i];
-        for (int i = 0; i < 3; i++)
-            for (int k = 0; k < 3; k++) S.hitv[i * 3 + k] = 0.25 * P.v0 * P.hi[k * 3 + i];
-        S.v0 = P.v0;
-        S.v0q = 0.25 * P.v0;
         S.efree = P.efree;
+        if (P.v0 == 0.0) {  // unused slot
+            for (int i = 0; i < 36; i++) S.Bq[i] = 0.0;
+            for (int i = 0; i < 6; i++) S.c0[i] = 0.0;
+            continue;
+        }
+        // K: Voigt form of d -> hi d hi^T (shear columns doubled);  Kp: Voigt form of s -> hi^T s hi
+        long double K[6][6], Kp[6][6], AK[6][6];
+        for (int I = 0; I < 6; I++)
+            for (int J = 0; J < 6; J++) {
+                const int a = vi[I], b = vj[I], k = vi[J], l = vj[J];
+                K[I][J] = (long double)P.hi[a * 3 + k] * P.hi[b * 3 + l];
+                if (k != l) K[I][J] += (long double)P.hi[a * 3 + l] * P.hi[b * 3 + k];
+                // Kp[J'][I']: J' = (a, b) is the output entry, I' = (k, l) the input entry
+                Kp[I][J] = (long double)P.hi[k * 3 + a] * P.hi[l * 3 + b];
+                if (k != l) Kp[I][J] += (long double)P.hi[l * 3 + a] * P.hi[k * 3 + b];
+            }
+        for (int I = 0; I < 6; I++)
+            for (int J = 0; J < 6; J++) {
+                long double acc = 0.0L;
+                for (int M = 0; M < 6; M++) acc += (long double)P.A[I * 6 + M] * K[M][J];
+                AK[I][J] = acc;
+            }
+        for (int I = 0; I < 6; I++)
+            for (int J = 0; J < 6; J++) {
+                long double acc = 0.0L;
+                for (int M = 0; M < 6; M++) acc += Kp[I][M] * AK[M][J];
+                // eps = 1/2 K (c - c0), c = Hs Hs^T / 16, Sq = V0/16 hi^T s hi  ->  1/2 * 1/16 * 1/16
+                S.Bq[I * 6 + J] = (double)(acc * (long double)P.v0 / 512.0L);
+            }
+        // c0 = h0 h0^T; h0 itself is not kept in StateP: invert hi (3x3 adjugate)
+        const double *m = P.hi;
+        const long double det = (long double)m[0] * ((long double)m[4] * m[8] - (long double)m[5] * m[7]) -
+                                (long double)m[1] * ((long double)m[3] * m[8] - (long double)m[5] * m[6]) +
+                                (long double)m[2] * ((long double)m[3] * m[7] - (long double)m[4] * m[6]);
+        long double h0[9];
+        h0[0] = ((long double)m[4] * m[8] - (long double)m[5] * m[7]) / det;
+        h0[1] = ((long double)m[2] * m[7] - (long double)m[1] * m[8]) / det;
+        h0[2] = ((long double)m[1] * m[5] - (long double)m[2] * m[4]) / det;
+        h0[3] = ((long double)m[5] * m[6] - (long double)m[3] * m[8]) / det;
+        h0[4] = ((long double)m[0] * m[8] - (long double)m[2] * m[6]) / det;
+        h0[5] = ((long double)m[2] * m[3] - (long double)m[0] * m[5]) / det;
+        h0[6] = ((long double)m[3] * m[7] - (long double)m[4] * m[6]) / det;
+        h0[7] = ((long double)m[1] * m[6] - (long double)m[0] * m[7]) / det;
+        h0[8] = ((long double)m[0] * m[4] - (long double)m[1] * m[3]) / det;
+        for (int I = 0; I < 6; I++) {
+            const int a = vi[I], b = vj[I];
+            long double acc = 0.0L;
+            for (int j = 0; j < 3; j++) acc += h0[a * 3 + j] * h0[b * 3 + j];
+            S.c0[I] = (double)(16.0L * acc);
+        }
     }
 }
 
@@ -318,43 +363,42 @@ static void fill_args(mm_handle *h, MarchArgs &a) {
     a.minv = g.minv;
     a.type = g.type;
     a.sc = g.d_sc;
-    a.spd = g.d_sp;
     a.partials = g.d_partials;
 }
 
-template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, bool AHG, int TY>
+template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, bool PSYNC, int TY>
 static int launch_one(mm_handle *h, const MarchArgs &a, int write_g) {
     dim3 grid;
     sg_blocks(h, grid);
     prof_begin(h, STEP);
-    k_march<STEP, SINGLE, ROT, VM, LEAN, AHG, TY><<<grid, dim3(TX, TY), 0, h->stream>>>(h->sg.sp, a, write_g);
+    k_march<STEP, SINGLE, ROT, VM, LEAN, PSYNC, TY><<<grid, dim3(TX, TY), 0, h->stream>>>(h->sg.sp, a, write_g);
     prof_end(h);
     h->launches++;
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
 
-template <bool SINGLE, bool AHG>
+template <bool SINGLE, bool PSYNC>
 static int launch_sel(mm_handle *h, const MarchArgs &a, bool step, int rot, int vm, bool lean, int write_g) {
     constexpr int TY = 8;
     if (step) {
         if (lean) {
-            if (vm == 0) return launch_one<1, SINGLE, 0, 0, true, AHG, TY>(h, a, write_g);
-            return launch_one<1, SINGLE, 0, 1, true, AHG, TY>(h, a, write_g);
+            if (vm == 0) return launch_one<1, SINGLE, 0, 0, true, PSYNC, TY>(h, a, write_g);
+            return launch_one<1, SINGLE, 0, 1, true, PSYNC, TY>(h, a, write_g);
         }
-        if (vm == 0) return launch_one<1, SINGLE, 0, 0, false, AHG, TY>(h, a, write_g);
-        if (vm == 1) return launch_one<1, SINGLE, 0, 1, false, AHG, TY>(h, a, write_g);
-        return launch_one<1, SINGLE, 0, 2, false, AHG, TY>(h, a, write_g);
+        if (vm == 0) return launch_one<1, SINGLE, 0, 0, false, PSYNC, TY>(h, a, write_g);
+        if (vm == 1) return launch_one<1, SINGLE, 0, 1, false, PSYNC, TY>(h, a, write_g);
+        return launch_one<1, SINGLE, 0, 2, false, PSYNC, TY>(h, a, write_g);
     }
-    if (rot == 0) return launch_one<0, SINGLE, 0, 0, false, AHG, TY>(h, a, write_g);
-    if (rot == 1) return launch_one<0, SINGLE, 1, 0, false, AHG, TY>(h, a, write_g);
-    return launch_one<0, SINGLE, 2, 0, false, AHG, TY>(h, a, write_g);
+    if (rot == 0) return launch_one<0, SINGLE, 0, 0, false, PSYNC, TY>(h, a, write_g);
+    if (rot == 1) return launch_one<0, SINGLE, 1, 0, false, PSYNC, TY>(h, a, write_g);
+    return launch_one<0, SINGLE, 2, 0, false, PSYNC, TY>(h, a, write_g);
 }
 
 static int launch_march(mm_handle *h, const MarchArgs &a, bool step, int rot, int vm, bool lean, int write_g) {
     const bool single = h->sg.sp.ntypes == 1 && h->sg.sp.nstates[0] == 1;
     if (!single) return launch_sel<false, false>(h, a, step, rot, vm, false, write_g);
-    if (h->sg.ahg) return launch_sel<true, true>(h, a, step, rot, vm, lean, write_g);
+    if (h->sg.psync) return launch_sel<true, true>(h, a, step, rot, vm, lean, write_g);
     return launch_sel<true, false>(h, a, step, rot, vm, lean, write_g);
 }
 

@@ -7,15 +7,11 @@
 
 namespace mm {
 
-// Per-state constants pre-scaled for the marching kernel (all scalings are by powers of two -> exact):
-//   Hs = 4 H is what the separable stencil produces; G = hiq Hs; u = G G^T - I = 2 eps; s = Ah u = A eps;
-//   E = v0q (u:s);  D' = D / 4 = hitv (s G);  vir = v0 G^T (s G)
+// Per-state constants of the marching kernel (mm_march.cuh: metric formulation), folded on the host in fold_sparams:
+//   Hs = 4 H is what the separable stencil produces;  d = Hs Hs^T - c0;  Sq = Bq d;  E = 1/4 d:Sq;  D' = D / 4 = Sq Hs
 struct SState {
-    double hiq[9];   // h0^-1 / 4
-    double Ah[36];   // A / 2
-    double hitv[9];  // (V0 / 4) h0^-T     ([i][k] = V0/4 * hi[k][i])
-    double v0;       // V0
-    double v0q;      // V0 / 4
+    double Bq[36];   // V0/512 K' A K  (K, K': the congruences with h0^-1 in Voigt form)
+    double c0[6];    // 16 h0 h0^T, Voigt order 00 11 22 12 02 01
     double efree;
 };
 
@@ -58,7 +54,7 @@ struct SGrid {
     double *d_partials = nullptr;   // [nblocks][kRedSlots]
     int nblocks = 0, nblocks_alloc = 0;
     int tile_rows = 8;              // TY of the marching kernel (warps per block)
-    int ahg = 0;                    // tuning: elasticity block via global loads instead of uniform registers
+    int psync = 0;                  // tuning: pairwise named-barrier handshakes between tile rows instead of block barriers
     int chunk = 32;                 // owned planes per block along z
     SParams sp;
 };
@@ -74,7 +70,6 @@ struct MarchArgs {
     const double *m, *minv;
     const uint8_t *type;
     const StepConsts *sc;
-    const SParams *spd;  // the same parameters in global memory (for the non-hoistable elasticity loads)
     double *partials;
 };
 
