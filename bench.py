@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tile-rows", type=int, default=0, help="tuning: warps per block of the marching kernel (8/12/16)")
-    ap.add_argument("--psync", type=int, default=-1, help="tuning: pairwise named-barrier row handshakes in the marching kernel (0/1)")
+    ap.add_argument("--variant", type=int, default=-1, help="tuning bits of the marching kernel (1 pairwise barriers, 2 LDCU constants, 4 two planes per trip)")
     ap.add_argument("--generic", action="store_true", help="force the indexed-topology kernels (no structured path)")
     return ap.parse_args()
 
@@ -216,8 +216,8 @@ def main():
         part = ForcePartMechanical(system, model=args.model, device=local_rank, slab=layout.slab_arg())
     if args.tile_rows:
         _lib.check(lib.mm_set_option(part.handle, b"tile_rows", args.tile_rows))
-    if args.psync >= 0:
-        _lib.check(lib.mm_set_option(part.handle, b"psync", args.psync))
+    if args.variant >= 0:
+        _lib.check(lib.mm_set_option(part.handle, b"variant", args.variant))
     mmf = MicMecForceField(system, [part])
     stream = torch.cuda.Stream(device=local_rank)
     _lib.check(lib.mm_set_stream(part.handle, ctypes.c_void_p(stream.cuda_stream)))

@@ -374,8 +374,8 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value) {
         h->sg.active = 1;
         return MM_OK;
     }
-    if (strcmp(name, "psync") == 0) {
-        h->sg.psync = value ? 1 : 0;
+    if (strcmp(name, "variant") == 0) {
+        h->sg.variant = (int)value & 7;
         return MM_OK;
     }
     if (strcmp(name, "tile_rows") == 0) {

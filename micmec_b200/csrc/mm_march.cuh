@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <type_traits>
 
 #include "mm_reduce.cuh"
@@ -42,6 +43,47 @@ __device__ __forceinline__ void sstate_eval(const double d[6], const SState &P, 
     e = 0.25 * dens;
 }
 
+// The single-type fast path reads its 43 constants from a __constant__ slot INSIDE the plane loop.  FP64 instructions
+// of sm_100 take a constant operand only from a uniform register, the uniform file holds ~39 doubles, and ptxas
+// parks the overflow in vector registers (46 of them, plus one R2UR per use and plane).  An ld.const whose address
+// depends on the plane index (ca = slot base + (p & 0)) cannot be hoisted: it becomes one LDCU per use straight into
+// a short-lived uniform register, and the vector registers are free for the pipeline.
+constexpr int kConstSlots = 8;
+__constant__ SState c_sstate[kConstSlots];
+
+__device__ __forceinline__ void ldc2(size_t addr, double &a, double &b) {
+    asm volatile("ld.const.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(addr));
+}
+
+__device__ __forceinline__ void sstate_eval_const(const double Hs[9], size_t ca, double &e, double Sq[6]) {
+    constexpr size_t oB = offsetof(SState, Bq), oC = offsetof(SState, c0);
+    double c0[6];
+    ldc2(ca + oC, c0[0], c0[1]);
+    ldc2(ca + oC + 16, c0[2], c0[3]);
+    ldc2(ca + oC + 32, c0[4], c0[5]);
+    double d[6];
+    d[0] = fma(Hs[2], Hs[2], fma(Hs[1], Hs[1], fma(Hs[0], Hs[0], -c0[0])));
+    d[1] = fma(Hs[5], Hs[5], fma(Hs[4], Hs[4], fma(Hs[3], Hs[3], -c0[1])));
+    d[2] = fma(Hs[8], Hs[8], fma(Hs[7], Hs[7], fma(Hs[6], Hs[6], -c0[2])));
+    d[3] = fma(Hs[5], Hs[8], fma(Hs[4], Hs[7], fma(Hs[3], Hs[6], -c0[3])));
+    d[4] = fma(Hs[2], Hs[8], fma(Hs[1], Hs[7], fma(Hs[0], Hs[6], -c0[4])));
+    d[5] = fma(Hs[2], Hs[5], fma(Hs[1], Hs[4], fma(Hs[0], Hs[3], -c0[5])));
+#pragma unroll
+    for (int I = 0; I < 6; I++) {
+        double b0, b1, b2, b3, b4, b5;
+        ldc2(ca + oB + I * 48, b0, b1);
+        ldc2(ca + oB + I * 48 + 16, b2, b3);
+        ldc2(ca + oB + I * 48 + 32, b4, b5);
+        const double lo = fma(b2, d[2], fma(b1, d[1], b0 * d[0]));
+        Sq[I] = fma(b5, d[5], fma(b4, d[4], fma(b3, d[3], lo)));
+    }
+    const double dens = fma(2.0, fma(d[5], Sq[5], fma(d[4], Sq[4], d[3] * Sq[3])), fma(d[2], Sq[2], fma(d[1], Sq[1], d[0] * Sq[0])));
+    // efree is added once per owned cell column after the plane loop: a constant that enters an FMA as the ADDEND next to
+    // an immediate needs a vector register, and ptxas then moves the whole address chain (and with it every constant
+    // load of this function) from the uniform datapath to per-thread LDC instructions
+    e = 0.25 * dens;
+}
+
 // named barriers (PTX bar.arrive / bar.sync with a thread count): the producer-consumer handshake between two warps
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -50,12 +92,20 @@ __device__ __forceinline__ void bar_wait(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Predicated store without a branch.  The plane loop must stay free of divergent branches: ptxas only keeps the
+// constant loads (and the loop bookkeeping) on the uniform datapath where it can prove that the warp is converged.
+__device__ __forceinline__ void st_if(bool pred, double *addr, double v) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %0, 0; @q st.global.f64 [%1], %2; }" ::"r"((int)pred), "l"(addr), "d"(v) : "memory");
+}
+
 // all states of a cell, Boltzmann-mixed (mmff.py:377-398); the mixing is linear in the gradient, hence in Sq.
-template <bool SINGLE, bool WANT_VIR>
-__device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp, int type, double &e, double D[9],
-                                           double vir[6]) {
+template <bool SINGLE, bool CLDCU, bool WANT_VIR>
+__device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp, size_t ca, int type, double &e,
+                                           double D[9], double vir[6]) {
     double Sq[6];
-    if (SINGLE) {
+    if (SINGLE && CLDCU) {
+        sstate_eval_const(Hs, ca, e, Sq);
+    } else if (SINGLE) {
         const SState &P = kp.st[0];
         double d[6];
         d[0] = fma(Hs[2], Hs[2], fma(Hs[1], Hs[1], fma(Hs[0], Hs[0], -P.c0[0])));
@@ -64,8 +114,7 @@ __device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp
         d[3] = fma(Hs[5], Hs[8], fma(Hs[4], Hs[7], fma(Hs[3], Hs[6], -P.c0[3])));
         d[4] = fma(Hs[2], Hs[8], fma(Hs[1], Hs[7], fma(Hs[0], Hs[6], -P.c0[4])));
         d[5] = fma(Hs[2], Hs[5], fma(Hs[1], Hs[4], fma(Hs[0], Hs[3], -P.c0[5])));
-        sstate_eval(d, P, e, Sq);
-        e += P.efree;
+        sstate_eval(d, P, e, Sq);  // efree: added once per column after the loop, as in the LDCU variant
     } else {
         const int ns = kp.nstates[type], off = kp.offset[type];
         double c[6], d[6];
@@ -122,18 +171,27 @@ __device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp
 
 // Template parameters
 //   STEP    0 force only, 1 fused kick-drift-force-kick
-//   SINGLE  one cell type with one metastable state (no type lookups, virial scaled once per block)
+//   SINGLE  one cell type with one metastable state (constants from the __constant__ slot, no type lookups)
 //   ROT     FORCE only: 1 = positions are rotated on load (x_true = (x + shift) . Rpend); 2 = and written back
 //   VM      STEP only: pending velocity transform  0 none, 1 scalar (Mvel[0]), 2 full 3x3
 //   LEAN    no virial, kinetic-energy diagonal only (NVE / NVT steps whose pressure nobody looks at)
-//   PSYNC   neighbouring rows synchronise pairwise through named barriers instead of two block-wide barriers per plane
+//   VAR     tuning bits (measured in profiles/): 1 = neighbouring rows synchronise pairwise through named barriers instead
+//           of two block-wide barriers per plane; 2 = single-type constants by LDCU inside the loop; 4 = two planes per trip
 //   TY      tile rows (warps per block); the tile owns (TX-2) x (TY-2) node columns
-template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, bool PSYNC, int TY>
+//
+// Shared-memory / shuffle traffic per plane and thread (the LSU pipe is as scarce as the FP64 pipe here: measured
+// 1.0 / 2.0 / 2.5 cycles per warp instruction and SM for SHFL / STS.64 / LDS.64, profiles/microbench):
+//   forward   y first, on the raw position (3 STS + 3 LDS), then x on the y-sum / y-difference (6 doubles by shuffle)
+//   backward  x first, then y, adding rows of equal sign before each exchange: 6 doubles by shuffle, 3 STS + 3 LDS
+template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, int VAR, int TY>
 __global__ void __launch_bounds__(TX *TY, 1)
 k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a, const int write_g) {
     constexpr int OX = TX - 2, OY = TY - 2;
-    __shared__ double sf[6][TY][TX];  // forward exchange along y: (px, dx) of the row above
-    __shared__ double sb[9][TY][TX];  // backward exchange along y: z-combined D rows of the row below
+    constexpr bool PSYNC = (VAR & 1) != 0;   // pairwise named-barrier handshakes instead of block barriers
+    constexpr bool CLDCU = (VAR & 2) != 0;   // single-type constants by LDCU inside the loop instead of kernel parameters
+    constexpr int UNR = (VAR & 4) ? 2 : 1;   // planes per loop trip
+    __shared__ double sf[3][TY][TX];  // forward exchange along y: position of the row above
+    __shared__ double sb[3][TY][TX];  // backward exchange along y: x-combined gradient part of the row below
 
     const int lane = threadIdx.x, row = threadIdx.y;
     const int nx = a.nx, ny = a.ny;
@@ -160,23 +218,27 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     const int rowp = (row + 1 < TY) ? row + 1 : row;
     const int rowm = (row > 0) ? row - 1 : row;
 
-    const int64_t plane = (int64_t)nx * ny;
+    const size_t cbase = SINGLE ? __cvta_generic_to_constant(&c_sstate[a.cslot]) : 0;
+    unsigned zoff = 0;
+    // 32-bit element indices (the host refuses grids beyond 2^31 padded nodes per array): one IMAD.WIDE per address
+    const unsigned plane = (unsigned)nx * (unsigned)ny;
     const int c0 = 1 + blockIdx.z * a.chunk;
     const int c1 = min(c0 + a.chunk, a.nzl + 1);
-    int64_t idx = ((int64_t)(c0 - 1) * ny + ll) * nx + kk;  // node (kk, ll) in array plane p
+    unsigned idx = ((unsigned)(c0 - 1) * ny + ll) * nx + kk;  // node (kk, ll) in array plane p
 
     double acc[14];
 #pragma unroll
     for (int i = 0; i < 14; i++) acc[i] = 0.0;
 
     // carried from plane to plane
-    double fpxy[3], fdxy[3], fpyd[3];   // forward: xy-combined sums / differences of the previous plane
-    double Dp[9];                       // D' of the previous cell layer
+    double fpxy[3] = {0, 0, 0}, fdxy[3] = {0, 0, 0}, fpyd[3] = {0, 0, 0};  // forward: xy-combined sums / differences
+    double Dp[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};                            // D' of the previous cell layer
     double vh[3] = {0, 0, 0}, mprev = 0.0, hminv_prev = 0.0;  // STEP: half-kicked velocity / mass of the previous plane
 
-    // software pipeline: raw loads of the NEXT plane are issued before the arithmetic of the current one
+    // software pipeline: raw loads of the NEXT plane are issued before the arithmetic of the current one (the arrays
+    // carry one spare plane, so the prefetch of the last iteration stays inside the allocation)
     double nx_[3], nv_[3], ng_[3], nm_ = 0.0, nminv_ = 0.0;
-    auto issue_loads = [&](int64_t at) {
+    auto issue_loads = [&](unsigned at) {
 #pragma unroll
         for (int d = 0; d < 3; d++) nx_[d] = a.x[d][at];
         if (STEP) {
@@ -191,8 +253,12 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     };
     issue_loads(idx);
 
-#pragma unroll 1
-    for (int p = c0 - 1; p <= c1; p++, idx += plane) {
+    // One plane.  CELL: cell layer p-1 (planes p-1 and p) exists; NODE: node plane p-1 (cell layers p-2, p-1) is
+    // completed.  The first two planes of a chunk are peeled (CELL / NODE false), so that the steady-state loop has no
+    // uniform branches and its constant loads stay on the uniform datapath.
+    auto plane_body = [&](auto cell_tag, auto node_tag, const int p) {
+        constexpr bool CELL = decltype(cell_tag)::value, NODE = decltype(node_tag)::value;
+        zoff = (zoff + (unsigned)a.zmask) & (unsigned)a.zmask;  // always 0, but loop-variant and uniform for ptxas
         const double cx0 = nx_[0], cx1 = nx_[1], cx2 = nx_[2];
         double cv[3], cg[3];
         const double cm = nm_, cminv = nminv_;
@@ -203,7 +269,7 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
                 cg[d] = ng_[d];
             }
         }
-        if (p < c1) issue_loads(idx + plane);
+        issue_loads(idx + plane);
 
         // ---- node (lane, row, p): true position (and, in STEP mode, kick + drift: verlet.py:144-146) -------------
         const double xs = cx0 + shx, ys = cx1 + shy, zs = cx2 + shz;
@@ -229,21 +295,15 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
                 r[j] = fma(dt, vcur[j], r[j]);
             }
         }
-        if ((STEP || ROT == 2) && own_xy && p >= c0 && p < c1) {  // owned columns carry no periodic shift
+        if ((STEP || ROT == 2) && CELL) {  // owned columns carry no periodic shift
+            const bool px = own_xy && p < c1;
 #pragma unroll
-            for (int j = 0; j < 3; j++) a.xo[j][idx] = r[j];
+            for (int j = 0; j < 3; j++) st_if(px, a.xo[j] + idx, r[j]);
         }
 
-        // ---- forward butterfly: x by shuffle, y through shared memory, z in registers ------------------------------
-        double px[3], dx[3];
+        // ---- forward butterfly: y through shared memory, x by shuffle, z in registers -------------------------------
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const double rn = __shfl_down_sync(0xffffffffu, r[j], 1);
-            px[j] = rn + r[j];
-            dx[j] = rn - r[j];
-            sf[j][row][lane] = px[j];
-            sf[3 + j][row][lane] = dx[j];
-        }
+        for (int j = 0; j < 3; j++) sf[j][row][lane] = r[j];
         if (PSYNC) {  // row r only needs row r+1: producer arrives, consumer waits (barrier ids 1 .. TY-1)
             if (row > 0) bar_arrive(row, 2 * TX);
             if (row + 1 < TY) bar_wait(row + 1, 2 * TX);
@@ -253,16 +313,16 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         double pxy[3], dxy[3], pyd[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            const double pxn = sf[j][rowp][lane], dxn = sf[3 + j][rowp][lane];
-            pxy[j] = px[j] + pxn;
-            dxy[j] = dx[j] + dxn;
-            pyd[j] = pxn - px[j];
+            const double rn = sf[j][rowp][lane];
+            const double py = rn + r[j], dy = rn - r[j];
+            const double pyn = __shfl_down_sync(0xffffffffu, py, 1), dyn = __shfl_down_sync(0xffffffffu, dy, 1);
+            pxy[j] = py + pyn;   // sum over the four nodes of the cell face in this plane
+            dxy[j] = pyn - py;   // x difference of the y sums
+            pyd[j] = dy + dyn;   // y difference of the x sums
         }
 
-        const bool have_cell = p >= c0;       // cell layer p-1 (planes p-1 and p)
-        const bool have_node = p >= c0 + 1;   // node plane p-1 (cell layers p-2 and p-1)
         double D[9];
-        if (have_cell) {
+        if (CELL) {
             double Hs[9];
 #pragma unroll
             for (int j = 0; j < 3; j++) {
@@ -272,12 +332,12 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             }
             const int type = SINGLE ? 0 : (int)a.type[idx - plane];
             double e, vir[6];
-            scell_eval<SINGLE, !LEAN>(Hs, kp, type, e, D, vir);
-            if (own_xy && have_node) {  // the warm-up layer c0-1 belongs to the chunk below
-                acc[0] += e;
+            scell_eval<SINGLE, CLDCU, !LEAN>(Hs, kp, cbase + zoff, type, e, D, vir);
+            if (NODE) {  // the warm-up layer c0-1 belongs to the chunk below
+                acc[0] += own_xy ? e : 0.0;
                 if (!LEAN) {
 #pragma unroll
-                    for (int q = 0; q < 6; q++) acc[1 + q] += vir[q];
+                    for (int q = 0; q < 6; q++) acc[1 + q] += own_xy ? vir[q] : 0.0;
                 }
             }
         }
@@ -288,17 +348,21 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             fpyd[j] = pyd[j];
         }
 
-        // ---- backward butterfly: z in registers, y through shared memory, x by shuffle ---------------------------
-        double P[9];  // z-combined rows of this thread's cell column: kept in registers across the barrier
-        if (have_node) {
+        // ---- backward butterfly: z in registers, x by shuffle, y through shared memory -----------------------------
+        // With p0, p1, p2 the z-combined rows of a cell column, the node gathers  (+ lane-1, - lane) of p0, (+ row-1, - row)
+        // of p1 and all four p2.  Adding what has equal sign BEFORE each exchange leaves 2 doubles per component for the
+        // shuffle (p0 + p2 and p1) and 1 for shared memory (ya + yb):
+        //   ya = (p0 + p2)[lane-1] + (p2 - p0),  yb = p1[lane-1] + p1,   g = (ya + yb)[row-1] + (ya - yb)
+        double gd[3];  // ya - yb: the own row's part of the gradient
+        if (NODE) {
 #pragma unroll
             for (int j = 0; j < 3; j++) {
-                P[j] = Dp[j] + D[j];
-                P[3 + j] = Dp[3 + j] + D[3 + j];
-                P[6 + j] = Dp[6 + j] - D[6 + j];
-                sb[j][row][lane] = P[j];
-                sb[3 + j][row][lane] = P[3 + j];
-                sb[6 + j][row][lane] = P[6 + j];
+                const double p0 = Dp[j] + D[j], p1 = Dp[3 + j] + D[3 + j], p2 = Dp[6 + j] - D[6 + j];
+                const double s02m = __shfl_up_sync(0xffffffffu, p0 + p2, 1);
+                const double p1m = __shfl_up_sync(0xffffffffu, p1, 1);
+                const double ya = s02m + (p2 - p0), yb = p1m + p1;
+                sb[j][row][lane] = ya + yb;
+                gd[j] = ya - yb;
             }
         }
         if (PSYNC) {  // row r only needs row r-1 (barrier ids TY .. 2 TY - 2); these two handshakes per plane also order
@@ -308,44 +372,35 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         } else {
             __syncthreads();
         }
-        if (have_node) {
+        if (NODE) {
             double g[3];
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const double q0 = sb[j][rowm][lane] + P[j];
-                const double q1 = sb[3 + j][rowm][lane] - P[3 + j];
-                const double q2 = sb[6 + j][rowm][lane] + P[6 + j];
-                const double s12 = q1 + q2;
-                const double q0m = __shfl_up_sync(0xffffffffu, q0, 1), s12m = __shfl_up_sync(0xffffffffu, s12, 1);
-                g[j] = (q0m - q0) + (s12m + s12);
-            }
-            if (own_xy) {
-                const int64_t at = idx - plane;
-                if (STEP) {  // second kick (verlet.py:152-153) + kinetic moments of the new velocities
-                    double vn[3];
+            for (int j = 0; j < 3; j++) g[j] = sb[j][rowm][lane] + gd[j];
+            const unsigned at = idx - plane;
+            if (STEP) {  // second kick (verlet.py:152-153) + kinetic moments of the new velocities
+                double vn[3];
 #pragma unroll
-                    for (int j = 0; j < 3; j++) {
-                        vn[j] = fma(-hminv_prev, g[j], vh[j]);
-                        a.vo[j][at] = vn[j];
-                    }
-                    const double mx = mprev * vn[0], my = mprev * vn[1], mz = mprev * vn[2];
-                    acc[7] = fma(mx, vn[0], acc[7]);
-                    acc[8] = fma(my, vn[1], acc[8]);
-                    acc[9] = fma(mz, vn[2], acc[9]);
-                    if (!LEAN) {
-                        acc[10] = fma(my, vn[2], acc[10]);
-                        acc[11] = fma(mx, vn[2], acc[11]);
-                        acc[12] = fma(mx, vn[1], acc[12]);
-                    }
+                for (int j = 0; j < 3; j++) {
+                    vn[j] = fma(-hminv_prev, g[j], vh[j]);
+                    st_if(own_xy, a.vo[j] + at, vn[j]);
                 }
-                if (write_g) {
-#pragma unroll
-                    for (int j = 0; j < 3; j++) a.go[j][at] = g[j];
+                const double mo = own_xy ? mprev : 0.0;
+                const double mx = mo * vn[0], my = mo * vn[1], mz = mo * vn[2];
+                acc[7] = fma(mx, vn[0], acc[7]);
+                acc[8] = fma(my, vn[1], acc[8]);
+                acc[9] = fma(mz, vn[2], acc[9]);
+                if (!LEAN) {
+                    acc[10] = fma(my, vn[2], acc[10]);
+                    acc[11] = fma(mx, vn[2], acc[11]);
+                    acc[12] = fma(mx, vn[1], acc[12]);
                 }
-                if (!LEAN) acc[13] += fma(g[0], g[0], fma(g[1], g[1], g[2] * g[2]));
             }
+            const bool pg = own_xy && write_g;
+#pragma unroll
+            for (int j = 0; j < 3; j++) st_if(pg, a.go[j] + at, g[j]);
+            if (!LEAN) acc[13] += own_xy ? fma(g[0], g[0], fma(g[1], g[1], g[2] * g[2])) : 0.0;
         }
-        if (have_cell) {
+        if (CELL) {
 #pragma unroll
             for (int q = 0; q < 9; q++) Dp[q] = D[q];
         }
@@ -355,8 +410,16 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             mprev = cm;
             hminv_prev = hminv;
         }
-    }
+        idx += plane;
+    };
 
+    plane_body(std::false_type{}, std::false_type{}, c0 - 1);
+    plane_body(std::true_type{}, std::false_type{}, c0);
+    // two planes per trip: the plane-to-plane hand-over of the carried values becomes register renaming instead of ~34 MOVs
+#pragma unroll UNR
+    for (int p = c0 + 1; p <= c1; p++) plane_body(std::true_type{}, std::true_type{}, p);
+
+    if (SINGLE && own_xy) acc[0] = fma((double)(c1 - c0), kp.st[0].efree, acc[0]);  // see sstate_eval_const
     // block reduction: warp shuffles, then one warp over the per-warp sums
     __shared__ double red[TY][14];
 #pragma unroll

@@ -21,6 +21,7 @@
 // Apron cells are recomputed by neighbouring blocks (tile 32 x TY threads -> 30 x (TY-2) owned nodes): the price of
 // never materialising per-cell data.  DESIGN.md discusses the trade-off and the measured numbers.  The kernel itself
 // lives in mm_march.cuh; this file holds the layout conversions, halo planes and the launch logic.
+#include <mutex>
 #include <vector>
 
 #include "mm_internal.h"
@@ -192,6 +193,28 @@ static void fold_sparams(const KParams &kp, SParams &sp) {
     }
 }
 
+// __constant__ slots of the single-type constants (c_sstate in mm_march.cuh): one table per device and process
+static std::mutex g_slot_mutex;
+static const mm_handle *g_slot_owner[64][kConstSlots] = {{nullptr}};
+
+static int slot_acquire(const mm_handle *h) {
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    const int dev = h->device & 63;
+    for (int s = 0; s < kConstSlots; s++)
+        if (!g_slot_owner[dev][s]) {
+            g_slot_owner[dev][s] = h;
+            return s;
+        }
+    return -1;  // all taken: the handle runs the general (multi-type) kernel variant instead
+}
+
+static void slot_release(const mm_handle *h) {
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    const int dev = h->device & 63;
+    for (int s = 0; s < kConstSlots; s++)
+        if (g_slot_owner[dev][s] == h) g_slot_owner[dev][s] = nullptr;
+}
+
 bool sg_eligible(const mm_handle *h) {
     return h->structured && h->model == MM_MODEL_ORIGINAL && h->nx >= 2 && h->ny >= 2 && h->nz >= 2;
 }
@@ -212,7 +235,7 @@ int sg_setup(mm_handle *h) {
     // (x = k fastest, y = l, z = m slowest): the marching direction is the reference's third axis, the lanes run along
     // its first axis.
     g.plane = (int64_t)g.nx * g.ny;
-    g.npad = g.plane * (g.nzl + 2);
+    g.npad = g.plane * (g.nzl + 3);  // two halo planes + one spare plane for the prefetch of the marching kernel
     fold_sparams(h->kp, g.sp);
     const size_t bytes = sizeof(double) * g.npad;
     for (int c = 0; c < 2; c++)
@@ -232,6 +255,13 @@ int sg_setup(mm_handle *h) {
     MM_CUDA(cudaMalloc(&g.d_sc, sizeof(StepConsts)));
     MM_CUDA(cudaMalloc(&g.d_sp, sizeof(SParams)));
     MM_CUDA(cudaMemcpyAsync(g.d_sp, &g.sp, sizeof(SParams), cudaMemcpyHostToDevice, h->stream));
+    g.cslot = -1;
+    if (g.sp.ntypes == 1 && g.sp.nstates[0] == 1) {
+        g.cslot = slot_acquire(h);
+        if (g.cslot >= 0)
+            MM_CUDA(cudaMemcpyToSymbolAsync(c_sstate, &g.sp.st[0], sizeof(SState), sizeof(SState) * g.cslot,
+                                            cudaMemcpyHostToDevice, h->stream));
+    }
     MM_CUDA(cudaStreamSynchronize(h->stream));
     MM_CUDA(cudaHostAlloc(&g.h_sc, sizeof(StepConsts), cudaHostAllocDefault));
     // chunk length along z: enough blocks for >= 4 waves of one block per SM, but no shorter than 8 planes
@@ -264,6 +294,8 @@ void sg_free(mm_handle *h) {
     cudaFree(g.d_sp);
     cudaFree(g.d_partials);
     if (g.h_sc) cudaFreeHost(g.h_sc);
+    slot_release(h);
+    g.cslot = -1;
     g.active = 0;
 }
 
@@ -364,42 +396,52 @@ static void fill_args(mm_handle *h, MarchArgs &a) {
     a.type = g.type;
     a.sc = g.d_sc;
     a.partials = g.d_partials;
+    a.cslot = g.cslot < 0 ? 0 : g.cslot;
+    a.zmask = 0;
 }
 
-template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, bool PSYNC, int TY>
+template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, int VAR, int TY>
 static int launch_one(mm_handle *h, const MarchArgs &a, int write_g) {
     dim3 grid;
     sg_blocks(h, grid);
     prof_begin(h, STEP);
-    k_march<STEP, SINGLE, ROT, VM, LEAN, PSYNC, TY><<<grid, dim3(TX, TY), 0, h->stream>>>(h->sg.sp, a, write_g);
+    k_march<STEP, SINGLE, ROT, VM, LEAN, VAR, TY><<<grid, dim3(TX, TY), 0, h->stream>>>(h->sg.sp, a, write_g);
     prof_end(h);
     h->launches++;
     MM_CUDA(cudaGetLastError());
     return MM_OK;
 }
 
-template <bool SINGLE, bool PSYNC>
+template <bool SINGLE, int VAR>
 static int launch_sel(mm_handle *h, const MarchArgs &a, bool step, int rot, int vm, bool lean, int write_g) {
     constexpr int TY = 8;
     if (step) {
         if (lean) {
-            if (vm == 0) return launch_one<1, SINGLE, 0, 0, true, PSYNC, TY>(h, a, write_g);
-            return launch_one<1, SINGLE, 0, 1, true, PSYNC, TY>(h, a, write_g);
+            if (vm == 0) return launch_one<1, SINGLE, 0, 0, true, VAR, TY>(h, a, write_g);
+            return launch_one<1, SINGLE, 0, 1, true, VAR, TY>(h, a, write_g);
         }
-        if (vm == 0) return launch_one<1, SINGLE, 0, 0, false, PSYNC, TY>(h, a, write_g);
-        if (vm == 1) return launch_one<1, SINGLE, 0, 1, false, PSYNC, TY>(h, a, write_g);
-        return launch_one<1, SINGLE, 0, 2, false, PSYNC, TY>(h, a, write_g);
+        if (vm == 0) return launch_one<1, SINGLE, 0, 0, false, VAR, TY>(h, a, write_g);
+        if (vm == 1) return launch_one<1, SINGLE, 0, 1, false, VAR, TY>(h, a, write_g);
+        return launch_one<1, SINGLE, 0, 2, false, VAR, TY>(h, a, write_g);
     }
-    if (rot == 0) return launch_one<0, SINGLE, 0, 0, false, PSYNC, TY>(h, a, write_g);
-    if (rot == 1) return launch_one<0, SINGLE, 1, 0, false, PSYNC, TY>(h, a, write_g);
-    return launch_one<0, SINGLE, 2, 0, false, PSYNC, TY>(h, a, write_g);
+    if (rot == 0) return launch_one<0, SINGLE, 0, 0, false, VAR, TY>(h, a, write_g);
+    if (rot == 1) return launch_one<0, SINGLE, 1, 0, false, VAR, TY>(h, a, write_g);
+    return launch_one<0, SINGLE, 2, 0, false, VAR, TY>(h, a, write_g);
 }
 
 static int launch_march(mm_handle *h, const MarchArgs &a, bool step, int rot, int vm, bool lean, int write_g) {
-    const bool single = h->sg.sp.ntypes == 1 && h->sg.sp.nstates[0] == 1;
-    if (!single) return launch_sel<false, false>(h, a, step, rot, vm, false, write_g);
-    if (h->sg.psync) return launch_sel<true, true>(h, a, step, rot, vm, lean, write_g);
-    return launch_sel<true, false>(h, a, step, rot, vm, lean, write_g);
+    const bool single = h->sg.cslot >= 0;  // one type, one state, and a __constant__ slot for its constants
+    if (!single) return launch_sel<false, 0>(h, a, step, rot, vm, false, write_g);
+    switch (h->sg.variant & 7) {
+        case 1: return launch_sel<true, 1>(h, a, step, rot, vm, lean, write_g);
+        case 2: return launch_sel<true, 2>(h, a, step, rot, vm, lean, write_g);
+        case 3: return launch_sel<true, 3>(h, a, step, rot, vm, lean, write_g);
+        case 4: return launch_sel<true, 4>(h, a, step, rot, vm, lean, write_g);
+        case 5: return launch_sel<true, 5>(h, a, step, rot, vm, lean, write_g);
+        case 6: return launch_sel<true, 6>(h, a, step, rot, vm, lean, write_g);
+        case 7: return launch_sel<true, 7>(h, a, step, rot, vm, lean, write_g);
+        default: return launch_sel<true, 0>(h, a, step, rot, vm, lean, write_g);
+    }
 }
 
 // Force evaluation at the stored positions.  rot: 0 = positions are true as stored, 1 = apply the pending rotation

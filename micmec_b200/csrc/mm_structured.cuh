@@ -54,13 +54,16 @@ struct SGrid {
     double *d_partials = nullptr;   // [nblocks][kRedSlots]
     int nblocks = 0, nblocks_alloc = 0;
     int tile_rows = 8;              // TY of the marching kernel (warps per block)
-    int psync = 0;                  // tuning: pairwise named-barrier handshakes between tile rows instead of block barriers
+    int variant = 0;                // tuning bits of the marching kernel (k_march VAR)
     int chunk = 32;                 // owned planes per block along z
+    int cslot = -1;                 // __constant__ slot holding sp.st[0] (single-type grids)
     SParams sp;
 };
 
 struct MarchArgs {
     int nx, ny, nzl, chunk;
+    int cslot;   // __constant__ slot of the single-type constants (mm_march.cuh: c_sstate)
+    int zmask;   // always 0: keeps the constant loads of the plane loop loop-variant (see ldc2)
     const double *x[3];
     double *xo[3];
     const double *v[3];
