@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libmicmec_b200.so")
+# MICMEC_B200_LIB: load another build of the same sources (used only by the ablation timings under profiles/)
+LIBPATH = os.environ.get("MICMEC_B200_LIB") or os.path.join(HERE, "libmicmec_b200.so")
 
 MM_OK, MM_ERR_INVALID, MM_ERR_CUDA, MM_ERR_NAN, MM_ERR_STATE = 0, -1, -2, -3, -4
 MM_HOST, MM_DEVICE = 0, 1

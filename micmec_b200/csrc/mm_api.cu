@@ -374,8 +374,19 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value) {
         h->sg.active = 1;
         return MM_OK;
     }
+    if (strcmp(name, "pf_dist") == 0) {
+        h->sg.pf_dist = (int)value < 1 ? 1 : (int)value;
+        return MM_OK;
+    }
     if (strcmp(name, "variant") == 0) {
-        h->sg.variant = (int)value & 7;
+        h->sg.variant = (int)value & 15;
+        return MM_OK;
+    }
+    if (strcmp(name, "chunk") == 0) {
+        if (!h->sg.d_sc) return MM_OK;
+        MM_CUDA(cudaSetDevice(h->device));
+        MM_CUDA(cudaStreamSynchronize(h->stream));
+        if (sg_set_chunk(h, (int)value) != MM_OK) return invalid("mm_set_option: chunk must be positive");
         return MM_OK;
     }
     if (strcmp(name, "tile_rows") == 0) {

@@ -113,6 +113,7 @@ int sg_to_aos(mm_handle *h, int which, double *d_aos);
 int sg_force(mm_handle *h, bool write_g, int rot);
 int sg_step(mm_handle *h, bool write_g, int vm, bool lean);
 int sg_set_tile_rows(mm_handle *h, int rows);
+int sg_set_chunk(mm_handle *h, int chunk);
 
 // ---- mm_comm.cu ---------------------------------------------------------------------------------------------
 int comm_halo(mm_handle *h, double **fields, int nfields, int npos);

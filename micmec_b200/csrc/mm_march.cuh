@@ -11,6 +11,14 @@
 namespace mm {
 
 constexpr int TX = 32;  // lanes along x: one warp per tile row
+constexpr int kStages = 4;   // planes in flight in the staged (bulk-copy) variant
+constexpr int kRowW = 36;    // doubles per staged row (34 used)
+// MM_ABLATE (profiles/ablation.sh only, never in the product build): remove one ingredient of k_march to time the rest.
+// 1 no barriers, 2 no shared-memory exchange (and no barriers), 4 no cell arithmetic, 8 no shuffles, 16 no global stores,
+// 32 no global loads after the first plane.  Results are meaningless; only the launch time is looked at.
+#ifndef MM_ABLATE
+#define MM_ABLATE 0
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 // One state of one cell from Hs = 4 H (rows = summed edge vectors).  The reference chain (nanocell_original.py:69-132)
@@ -43,47 +51,6 @@ __device__ __forceinline__ void sstate_eval(const double d[6], const SState &P, 
     e = 0.25 * dens;
 }
 
-// The single-type fast path reads its 43 constants from a __constant__ slot INSIDE the plane loop.  FP64 instructions
-// of sm_100 take a constant operand only from a uniform register, the uniform file holds ~39 doubles, and ptxas
-// parks the overflow in vector registers (46 of them, plus one R2UR per use and plane).  An ld.const whose address
-// depends on the plane index (ca = slot base + (p & 0)) cannot be hoisted: it becomes one LDCU per use straight into
-// a short-lived uniform register, and the vector registers are free for the pipeline.
-constexpr int kConstSlots = 8;
-__constant__ SState c_sstate[kConstSlots];
-
-__device__ __forceinline__ void ldc2(size_t addr, double &a, double &b) {
-    asm volatile("ld.const.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(addr));
-}
-
-__device__ __forceinline__ void sstate_eval_const(const double Hs[9], size_t ca, double &e, double Sq[6]) {
-    constexpr size_t oB = offsetof(SState, Bq), oC = offsetof(SState, c0);
-    double c0[6];
-    ldc2(ca + oC, c0[0], c0[1]);
-    ldc2(ca + oC + 16, c0[2], c0[3]);
-    ldc2(ca + oC + 32, c0[4], c0[5]);
-    double d[6];
-    d[0] = fma(Hs[2], Hs[2], fma(Hs[1], Hs[1], fma(Hs[0], Hs[0], -c0[0])));
-    d[1] = fma(Hs[5], Hs[5], fma(Hs[4], Hs[4], fma(Hs[3], Hs[3], -c0[1])));
-    d[2] = fma(Hs[8], Hs[8], fma(Hs[7], Hs[7], fma(Hs[6], Hs[6], -c0[2])));
-    d[3] = fma(Hs[5], Hs[8], fma(Hs[4], Hs[7], fma(Hs[3], Hs[6], -c0[3])));
-    d[4] = fma(Hs[2], Hs[8], fma(Hs[1], Hs[7], fma(Hs[0], Hs[6], -c0[4])));
-    d[5] = fma(Hs[2], Hs[5], fma(Hs[1], Hs[4], fma(Hs[0], Hs[3], -c0[5])));
-#pragma unroll
-    for (int I = 0; I < 6; I++) {
-        double b0, b1, b2, b3, b4, b5;
-        ldc2(ca + oB + I * 48, b0, b1);
-        ldc2(ca + oB + I * 48 + 16, b2, b3);
-        ldc2(ca + oB + I * 48 + 32, b4, b5);
-        const double lo = fma(b2, d[2], fma(b1, d[1], b0 * d[0]));
-        Sq[I] = fma(b5, d[5], fma(b4, d[4], fma(b3, d[3], lo)));
-    }
-    const double dens = fma(2.0, fma(d[5], Sq[5], fma(d[4], Sq[4], d[3] * Sq[3])), fma(d[2], Sq[2], fma(d[1], Sq[1], d[0] * Sq[0])));
-    // efree is added once per owned cell column after the plane loop: a constant that enters an FMA as the ADDEND next to
-    // an immediate needs a vector register, and ptxas then moves the whole address chain (and with it every constant
-    // load of this function) from the uniform datapath to per-thread LDC instructions
-    e = 0.25 * dens;
-}
-
 // named barriers (PTX bar.arrive / bar.sync with a thread count): the producer-consumer handshake between two warps
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -95,17 +62,37 @@ __device__ __forceinline__ void bar_wait(int id, int nthreads) {
 // Predicated store without a branch.  The plane loop must stay free of divergent branches: ptxas only keeps the
 // constant loads (and the loop bookkeeping) on the uniform datapath where it can prove that the warp is converged.
 __device__ __forceinline__ void st_if(bool pred, double *addr, double v) {
+    if (MM_ABLATE & 16) pred = pred && v == 1.2345e301;  // ablation build: keep the value alive, never store
     asm volatile("{ .reg .pred q; setp.ne.b32 q, %0, 0; @q st.global.f64 [%1], %2; }" ::"r"((int)pred), "l"(addr), "d"(v) : "memory");
 }
 
+// ---- bulk asynchronous copies global -> shared memory, completion on an mbarrier (PTX cp.async.bulk / mbarrier) ----------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
+}
+
 // all states of a cell, Boltzmann-mixed (mmff.py:377-398); the mixing is linear in the gradient, hence in Sq.
-template <bool SINGLE, bool CLDCU, bool WANT_VIR>
-__device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp, size_t ca, int type, double &e,
-                                           double D[9], double vir[6]) {
+template <bool SINGLE, bool WANT_VIR>
+__device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp, int type, double &e, double D[9],
+                                           double vir[6]) {
     double Sq[6];
-    if (SINGLE && CLDCU) {
-        sstate_eval_const(Hs, ca, e, Sq);
-    } else if (SINGLE) {
+    if (SINGLE) {
         const SState &P = kp.st[0];
         double d[6];
         d[0] = fma(Hs[2], Hs[2], fma(Hs[1], Hs[1], fma(Hs[0], Hs[0], -P.c0[0])));
@@ -114,7 +101,7 @@ __device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp
         d[3] = fma(Hs[5], Hs[8], fma(Hs[4], Hs[7], fma(Hs[3], Hs[6], -P.c0[3])));
         d[4] = fma(Hs[2], Hs[8], fma(Hs[1], Hs[7], fma(Hs[0], Hs[6], -P.c0[4])));
         d[5] = fma(Hs[2], Hs[5], fma(Hs[1], Hs[4], fma(Hs[0], Hs[3], -P.c0[5])));
-        sstate_eval(d, P, e, Sq);  // efree: added once per column after the loop, as in the LDCU variant
+        sstate_eval(d, P, e, Sq);  // efree: added once per owned column after the plane loop
     } else {
         const int ns = kp.nstates[type], off = kp.offset[type];
         double c[6], d[6];
@@ -179,6 +166,14 @@ __device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp
 //           of two block-wide barriers per plane; 2 = single-type constants by LDCU inside the loop; 4 = two planes per trip
 //   TY      tile rows (warps per block); the tile owns (TX-2) x (TY-2) node columns
 //
+// Loads (VAR & 2).  With one block of eight warps per SM and one plane of register prefetch, at most 8 x 11 x 256 B are in
+// flight per SM, far below what the HBM latency x bandwidth product asks for: the ablation in profiles/ shows the
+// kernel bound by exactly that (removing the loads saves 0.35 ms of 0.90, removing the cell arithmetic nothing).  The
+// staged variant keeps kStages planes of the tile in flight with bulk asynchronous copies (cp.async.bulk, one per field
+// row and periodic piece, 1-2 per thread, completion counted in bytes on an mbarrier per stage) into shared memory; the
+// threads then read their node with LDS.  A staged row holds the 34 nodes k0-1 .. k0+32 (the copy must start on a
+// 16-byte boundary, the tile starts on an odd node), split in two pieces where it crosses the periodic boundary.
+//
 // Shared-memory / shuffle traffic per plane and thread (the LSU pipe is as scarce as the FP64 pipe here: measured
 // 1.0 / 2.0 / 2.5 cycles per warp instruction and SM for SHFL / STS.64 / LDS.64, profiles/microbench):
 //   forward   y first, on the raw position (3 STS + 3 LDS), then x on the y-sum / y-difference (6 doubles by shuffle)
@@ -188,10 +183,14 @@ __global__ void __launch_bounds__(TX *TY, 1)
 k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a, const int write_g) {
     constexpr int OX = TX - 2, OY = TY - 2;
     constexpr bool PSYNC = (VAR & 1) != 0;   // pairwise named-barrier handshakes instead of block barriers
-    constexpr bool CLDCU = (VAR & 2) != 0;   // single-type constants by LDCU inside the loop instead of kernel parameters
+    constexpr bool TMA = (VAR & 2) != 0;     // node data staged by bulk async copies (NST planes in flight), see below
     constexpr int UNR = (VAR & 4) ? 2 : 1;   // planes per loop trip
+    constexpr bool PF2 = (VAR & 8) != 0;     // prefetch plane p + pf_dist into L2
+    constexpr int NF = STEP ? 11 : 3;        // staged fields per node: x (3) [, v (3), g (3), m, 1/m]
     __shared__ double sf[3][TY][TX];  // forward exchange along y: position of the row above
     __shared__ double sb[3][TY][TX];  // backward exchange along y: x-combined gradient part of the row below
+    __shared__ __align__(8) unsigned long long s_full[kStages];
+    extern __shared__ __align__(128) double s_stage[];  // TMA: [kStages][NF][TY][kRowW]
 
     const int lane = threadIdx.x, row = threadIdx.y;
     const int nx = a.nx, ny = a.ny;
@@ -218,8 +217,6 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     const int rowp = (row + 1 < TY) ? row + 1 : row;
     const int rowm = (row > 0) ? row - 1 : row;
 
-    const size_t cbase = SINGLE ? __cvta_generic_to_constant(&c_sstate[a.cslot]) : 0;
-    unsigned zoff = 0;
     // 32-bit element indices (the host refuses grids beyond 2^31 padded nodes per array): one IMAD.WIDE per address
     const unsigned plane = (unsigned)nx * (unsigned)ny;
     const int c0 = 1 + blockIdx.z * a.chunk;
@@ -251,25 +248,110 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             nminv_ = a.minv[at];
         }
     };
-    issue_loads(idx);
+    // staged variant: one copy job per thread = (field, tile row, periodic piece); the job's source for plane 0, its
+    // destination inside a stage and its size are fixed for the whole march
+    const int tid = row * TX + lane;
+    const double *job_src = nullptr;
+    unsigned job_dst = 0, job_bytes = 0;
+    unsigned it = 0;  // planes done: plane p = c0 - 1 + it lives in stage it % kStages, barrier phase (it / kStages) & 1
+    constexpr unsigned kStageDoubles = NF * TY * kRowW;
+    if (TMA) {
+        const int ks = blockIdx.x * OX - 2;  // first staged node of a row: even, so every piece starts on 16 bytes
+        const bool wraps = ks < 0 || ks + 34 > nx;
+        const int piece = tid & 1, jrow = (tid >> 1) % TY, f = tid / (2 * TY);
+        if (f < NF) {
+            const int lj = blockIdx.y * OY + jrow - 1;
+            const int qyj = (lj >= 0) ? lj / ny : -((-lj + ny - 1) / ny);
+            const int llj = lj - qyj * ny;
+            int a0 = 0, n = 0, slot = 0;
+            if (piece == 0) {
+                a0 = max(ks, 0);
+                n = min(ks + 34, nx) - a0;
+                slot = a0 - ks;
+            } else if (ks < 0) {  // nodes ks .. -1 are the last nodes of the row
+                a0 = nx + ks;
+                n = -ks;
+            } else if (ks + 34 > nx) {  // nodes nx .. ks+33 are the first nodes of the row
+                n = ks + 34 - nx;
+                slot = nx - ks;
+            }
+            const double *base = f < 3 ? a.x[f] : f < 6 ? a.v[f - 3] : f < 9 ? a.g[f - 6] : f == 9 ? a.m : a.minv;
+            job_src = base + ((size_t)llj * nx + a0);
+            job_dst = smem_u32(s_stage) + (unsigned)(((f * TY + jrow) * kRowW + slot) * 8);
+            job_bytes = (unsigned)n * 8u;
+        }
+        if (tid == 0) {
+            for (int st = 0; st < kStages; st++) mbar_init(smem_u32(&s_full[st]), NF * TY * (wraps ? 2 : 1));
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    auto stage_issue = [&](const int q, const unsigned st) {  // plane q -> stage st; every thread with a job arrives + copies
+        if (job_bytes) {
+            const unsigned bar = smem_u32(&s_full[st]);
+            mbar_arrive_expect(bar, job_bytes);
+            bulk_g2s(job_dst + st * (kStageDoubles * 8u), job_src + (size_t)q * plane, job_bytes, bar);
+        }
+    };
+    if (TMA) {
+        for (int st = 0; st < kStages; st++)
+            if (c0 - 1 + st <= c1) stage_issue(c0 - 1 + st, st);
+    } else {
+        issue_loads(idx);
+    }
 
     // One plane.  CELL: cell layer p-1 (planes p-1 and p) exists; NODE: node plane p-1 (cell layers p-2, p-1) is
     // completed.  The first two planes of a chunk are peeled (CELL / NODE false), so that the steady-state loop has no
     // uniform branches and its constant loads stay on the uniform datapath.
     auto plane_body = [&](auto cell_tag, auto node_tag, const int p) {
         constexpr bool CELL = decltype(cell_tag)::value, NODE = decltype(node_tag)::value;
-        zoff = (zoff + (unsigned)a.zmask) & (unsigned)a.zmask;  // always 0, but loop-variant and uniform for ptxas
-        const double cx0 = nx_[0], cx1 = nx_[1], cx2 = nx_[2];
-        double cv[3], cg[3];
-        const double cm = nm_, cminv = nminv_;
-        if (STEP) {
+        double cx0, cx1, cx2, cv[3] = {0, 0, 0}, cg[3] = {0, 0, 0}, cm = 0.0, cminv = 0.0;
+        const unsigned st = it % kStages;
+        if (TMA) {
+            mbar_wait(smem_u32(&s_full[st]), (it / kStages) & 1u);
+            const double *sp = s_stage + st * kStageDoubles + row * kRowW + lane + 1;  // node k0 + lane = staged slot lane + 1
+            cx0 = sp[0];
+            cx1 = sp[TY * kRowW];
+            cx2 = sp[2 * TY * kRowW];
+            if (STEP) {
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-                cv[d] = nv_[d];
-                cg[d] = ng_[d];
+                for (int d = 0; d < 3; d++) {
+                    cv[d] = sp[(3 + d) * TY * kRowW];
+                    cg[d] = sp[(6 + d) * TY * kRowW];
+                }
+                cm = sp[9 * TY * kRowW];
+                cminv = sp[10 * TY * kRowW];
+            }
+        } else {
+            cx0 = nx_[0];
+            cx1 = nx_[1];
+            cx2 = nx_[2];
+            cm = nm_;
+            cminv = nminv_;
+            if (STEP) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    cv[d] = nv_[d];
+                    cg[d] = ng_[d];
+                }
+            }
+            if (!(MM_ABLATE & 32)) issue_loads(idx + plane);
+            if (PF2 && p + a.pf_dist <= c1) {  // every lane: the L2 fills sectors (32 B), not lines
+                const unsigned at = idx + a.pf_dist * plane;
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x[d] + at));
+                    if (STEP) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.v[d] + at));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.g[d] + at));
+                    }
+                }
+                if (STEP) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.m + at));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.minv + at));
+                }
             }
         }
-        issue_loads(idx + plane);
 
         // ---- node (lane, row, p): true position (and, in STEP mode, kick + drift: verlet.py:144-146) -------------
         const double xs = cx0 + shx, ys = cx1 + shy, zs = cx2 + shz;
@@ -303,19 +385,23 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
 
         // ---- forward butterfly: y through shared memory, x by shuffle, z in registers -------------------------------
 #pragma unroll
-        for (int j = 0; j < 3; j++) sf[j][row][lane] = r[j];
-        if (PSYNC) {  // row r only needs row r+1: producer arrives, consumer waits (barrier ids 1 .. TY-1)
+        for (int j = 0; j < 3; j++)
+            if (!(MM_ABLATE & 2)) sf[j][row][lane] = r[j];
+        if (MM_ABLATE & 3) {
+        } else if (PSYNC) {  // row r only needs row r+1: producer arrives, consumer waits (barrier ids 1 .. TY-1)
             if (row > 0) bar_arrive(row, 2 * TX);
             if (row + 1 < TY) bar_wait(row + 1, 2 * TX);
         } else {
             __syncthreads();
         }
+        if (TMA && p + kStages <= c1) stage_issue(p + kStages, st);  // every thread has read stage st before the barrier
         double pxy[3], dxy[3], pyd[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            const double rn = sf[j][rowp][lane];
+            const double rn = (MM_ABLATE & 2) ? r[j] * 1.25 : sf[j][rowp][lane];
             const double py = rn + r[j], dy = rn - r[j];
-            const double pyn = __shfl_down_sync(0xffffffffu, py, 1), dyn = __shfl_down_sync(0xffffffffu, dy, 1);
+            const double pyn = (MM_ABLATE & 8) ? py * 1.5 : __shfl_down_sync(0xffffffffu, py, 1);
+            const double dyn = (MM_ABLATE & 8) ? dy * 0.75 : __shfl_down_sync(0xffffffffu, dy, 1);
             pxy[j] = py + pyn;   // sum over the four nodes of the cell face in this plane
             dxy[j] = pyn - py;   // x difference of the y sums
             pyd[j] = dy + dyn;   // y difference of the x sums
@@ -332,7 +418,15 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             }
             const int type = SINGLE ? 0 : (int)a.type[idx - plane];
             double e, vir[6];
-            scell_eval<SINGLE, CLDCU, !LEAN>(Hs, kp, cbase + zoff, type, e, D, vir);
+            if (MM_ABLATE & 4) {
+                e = Hs[0];
+#pragma unroll
+                for (int q = 0; q < 9; q++) D[q] = Hs[q];
+#pragma unroll
+                for (int q = 0; q < 6; q++) vir[q] = Hs[q];
+            } else {
+                scell_eval<SINGLE, !LEAN>(Hs, kp, type, e, D, vir);
+            }
             if (NODE) {  // the warm-up layer c0-1 belongs to the chunk below
                 acc[0] += own_xy ? e : 0.0;
                 if (!LEAN) {
@@ -358,14 +452,15 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
 #pragma unroll
             for (int j = 0; j < 3; j++) {
                 const double p0 = Dp[j] + D[j], p1 = Dp[3 + j] + D[3 + j], p2 = Dp[6 + j] - D[6 + j];
-                const double s02m = __shfl_up_sync(0xffffffffu, p0 + p2, 1);
-                const double p1m = __shfl_up_sync(0xffffffffu, p1, 1);
+                const double s02m = (MM_ABLATE & 8) ? (p0 + p2) * 1.5 : __shfl_up_sync(0xffffffffu, p0 + p2, 1);
+                const double p1m = (MM_ABLATE & 8) ? p1 * 0.75 : __shfl_up_sync(0xffffffffu, p1, 1);
                 const double ya = s02m + (p2 - p0), yb = p1m + p1;
-                sb[j][row][lane] = ya + yb;
+                if (!(MM_ABLATE & 2)) sb[j][row][lane] = ya + yb;
                 gd[j] = ya - yb;
             }
         }
-        if (PSYNC) {  // row r only needs row r-1 (barrier ids TY .. 2 TY - 2); these two handshakes per plane also order
+        if (MM_ABLATE & 3) {
+        } else if (PSYNC) {  // row r only needs row r-1 (barrier ids TY .. 2 TY - 2); these two handshakes per plane also order
                       // the reuse of sf / sb between planes
             if (row + 1 < TY) bar_arrive(TY + row, 2 * TX);
             if (row > 0) bar_wait(TY + row - 1, 2 * TX);
@@ -375,7 +470,7 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         if (NODE) {
             double g[3];
 #pragma unroll
-            for (int j = 0; j < 3; j++) g[j] = sb[j][rowm][lane] + gd[j];
+            for (int j = 0; j < 3; j++) g[j] = ((MM_ABLATE & 2) ? gd[j] * 1.25 : sb[j][rowm][lane]) + gd[j];
             const unsigned at = idx - plane;
             if (STEP) {  // second kick (verlet.py:152-153) + kinetic moments of the new velocities
                 double vn[3];
@@ -411,6 +506,7 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             hminv_prev = hminv;
         }
         idx += plane;
+        it++;
     };
 
     plane_body(std::false_type{}, std::false_type{}, c0 - 1);
@@ -419,7 +515,7 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
 #pragma unroll UNR
     for (int p = c0 + 1; p <= c1; p++) plane_body(std::true_type{}, std::true_type{}, p);
 
-    if (SINGLE && own_xy) acc[0] = fma((double)(c1 - c0), kp.st[0].efree, acc[0]);  // see sstate_eval_const
+    if (SINGLE && own_xy) acc[0] = fma((double)(c1 - c0), kp.st[0].efree, acc[0]);
     // block reduction: warp shuffles, then one warp over the per-warp sums
     __shared__ double red[TY][14];
 #pragma unroll
@@ -436,5 +532,6 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         a.partials[(size_t)bid * kRedSlots + lane] = s;
     }
 }
+
 
 }  // namespace mm

@@ -21,7 +21,6 @@
 // Apron cells are recomputed by neighbouring blocks (tile 32 x TY threads -> 30 x (TY-2) owned nodes): the price of
 // never materialising per-cell data.  DESIGN.md discusses the trade-off and the measured numbers.  The kernel itself
 // lives in mm_march.cuh; this file holds the layout conversions, halo planes and the launch logic.
-#include <mutex>
 #include <vector>
 
 #include "mm_internal.h"
@@ -193,28 +192,6 @@ static void fold_sparams(const KParams &kp, SParams &sp) {
     }
 }
 
-// __constant__ slots of the single-type constants (c_sstate in mm_march.cuh): one table per device and process
-static std::mutex g_slot_mutex;
-static const mm_handle *g_slot_owner[64][kConstSlots] = {{nullptr}};
-
-static int slot_acquire(const mm_handle *h) {
-    std::lock_guard<std::mutex> lock(g_slot_mutex);
-    const int dev = h->device & 63;
-    for (int s = 0; s < kConstSlots; s++)
-        if (!g_slot_owner[dev][s]) {
-            g_slot_owner[dev][s] = h;
-            return s;
-        }
-    return -1;  // all taken: the handle runs the general (multi-type) kernel variant instead
-}
-
-static void slot_release(const mm_handle *h) {
-    std::lock_guard<std::mutex> lock(g_slot_mutex);
-    const int dev = h->device & 63;
-    for (int s = 0; s < kConstSlots; s++)
-        if (g_slot_owner[dev][s] == h) g_slot_owner[dev][s] = nullptr;
-}
-
 bool sg_eligible(const mm_handle *h) {
     return h->structured && h->model == MM_MODEL_ORIGINAL && h->nx >= 2 && h->ny >= 2 && h->nz >= 2;
 }
@@ -255,13 +232,6 @@ int sg_setup(mm_handle *h) {
     MM_CUDA(cudaMalloc(&g.d_sc, sizeof(StepConsts)));
     MM_CUDA(cudaMalloc(&g.d_sp, sizeof(SParams)));
     MM_CUDA(cudaMemcpyAsync(g.d_sp, &g.sp, sizeof(SParams), cudaMemcpyHostToDevice, h->stream));
-    g.cslot = -1;
-    if (g.sp.ntypes == 1 && g.sp.nstates[0] == 1) {
-        g.cslot = slot_acquire(h);
-        if (g.cslot >= 0)
-            MM_CUDA(cudaMemcpyToSymbolAsync(c_sstate, &g.sp.st[0], sizeof(SState), sizeof(SState) * g.cslot,
-                                            cudaMemcpyHostToDevice, h->stream));
-    }
     MM_CUDA(cudaStreamSynchronize(h->stream));
     MM_CUDA(cudaHostAlloc(&g.h_sc, sizeof(StepConsts), cudaHostAllocDefault));
     // chunk length along z: enough blocks for >= 4 waves of one block per SM, but no shorter than 8 planes
@@ -294,8 +264,6 @@ void sg_free(mm_handle *h) {
     cudaFree(g.d_sp);
     cudaFree(g.d_partials);
     if (g.h_sc) cudaFreeHost(g.h_sc);
-    slot_release(h);
-    g.cslot = -1;
     g.active = 0;
 }
 
@@ -383,6 +351,7 @@ static void fill_args(mm_handle *h, MarchArgs &a) {
     a.ny = g.ny;
     a.nzl = g.nzl;
     a.chunk = g.chunk;
+    a.pf_dist = g.pf_dist;
     for (int d = 0; d < 3; d++) {
         a.x[d] = g.x[g.cx][d];
         a.xo[d] = g.x[g.cx ^ 1][d];
@@ -396,8 +365,6 @@ static void fill_args(mm_handle *h, MarchArgs &a) {
     a.type = g.type;
     a.sc = g.d_sc;
     a.partials = g.d_partials;
-    a.cslot = g.cslot < 0 ? 0 : g.cslot;
-    a.zmask = 0;
 }
 
 template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, int VAR, int TY>
@@ -405,7 +372,16 @@ static int launch_one(mm_handle *h, const MarchArgs &a, int write_g) {
     dim3 grid;
     sg_blocks(h, grid);
     prof_begin(h, STEP);
-    k_march<STEP, SINGLE, ROT, VM, LEAN, VAR, TY><<<grid, dim3(TX, TY), 0, h->stream>>>(h->sg.sp, a, write_g);
+    // staged variant: kStages planes of the tile in dynamic shared memory (opt-in above 48 KB, once per instantiation)
+    constexpr size_t dyn = (VAR & 2) ? sizeof(double) * kStages * (STEP ? 11 : 3) * TY * kRowW : 0;
+    if (dyn > 0) {
+        static bool configured[64] = {false};
+        if (!configured[h->device & 63]) {
+            MM_CUDA(cudaFuncSetAttribute(k_march<STEP, SINGLE, ROT, VM, LEAN, VAR, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            configured[h->device & 63] = true;
+        }
+    }
+    k_march<STEP, SINGLE, ROT, VM, LEAN, VAR, TY><<<grid, dim3(TX, TY), dyn, h->stream>>>(h->sg.sp, a, write_g);
     prof_end(h);
     h->launches++;
     MM_CUDA(cudaGetLastError());
@@ -430,16 +406,22 @@ static int launch_sel(mm_handle *h, const MarchArgs &a, bool step, int rot, int 
 }
 
 static int launch_march(mm_handle *h, const MarchArgs &a, bool step, int rot, int vm, bool lean, int write_g) {
-    const bool single = h->sg.cslot >= 0;  // one type, one state, and a __constant__ slot for its constants
+    const bool single = h->sg.sp.ntypes == 1 && h->sg.sp.nstates[0] == 1;
     if (!single) return launch_sel<false, 0>(h, a, step, rot, vm, false, write_g);
-    switch (h->sg.variant & 7) {
+    // staged loads need 16-byte aligned row pieces (nx even) and at most one periodic crossing per staged row
+    const bool stageable = h->sg.nx % 2 == 0 && h->sg.nx >= 64;
+    int var = h->sg.variant & 15;
+    if (!stageable) var &= ~2;
+    if (var & 2) var &= ~1;  // the refill of a stage relies on the block barrier
+    switch (var) {  // tuning variants kept for the measurements in profiles/ (bits: see k_march)
         case 1: return launch_sel<true, 1>(h, a, step, rot, vm, lean, write_g);
         case 2: return launch_sel<true, 2>(h, a, step, rot, vm, lean, write_g);
-        case 3: return launch_sel<true, 3>(h, a, step, rot, vm, lean, write_g);
         case 4: return launch_sel<true, 4>(h, a, step, rot, vm, lean, write_g);
         case 5: return launch_sel<true, 5>(h, a, step, rot, vm, lean, write_g);
         case 6: return launch_sel<true, 6>(h, a, step, rot, vm, lean, write_g);
-        case 7: return launch_sel<true, 7>(h, a, step, rot, vm, lean, write_g);
+        case 8: return launch_sel<true, 8>(h, a, step, rot, vm, lean, write_g);
+        case 9: return launch_sel<true, 9>(h, a, step, rot, vm, lean, write_g);
+        case 12: return launch_sel<true, 12>(h, a, step, rot, vm, lean, write_g);
         default: return launch_sel<true, 0>(h, a, step, rot, vm, lean, write_g);
     }
 }
@@ -469,6 +451,12 @@ int sg_step(mm_handle *h, bool write_g, int vm, bool lean) {
     g.cv ^= 1;
     if (write_g) g.cg ^= 1;
     return rc;
+}
+
+int sg_set_chunk(mm_handle *h, int chunk) {  // tuning: planes per block along z
+    if (chunk < 1) return MM_ERR_INVALID;
+    h->sg.chunk = chunk;
+    return sg_set_tile_rows(h, h->sg.tile_rows);
 }
 
 int sg_set_tile_rows(mm_handle *h, int rows) {

@@ -55,15 +55,14 @@ struct SGrid {
     int nblocks = 0, nblocks_alloc = 0;
     int tile_rows = 8;              // TY of the marching kernel (warps per block)
     int variant = 0;                // tuning bits of the marching kernel (k_march VAR)
+    int pf_dist = 3;                // L2 prefetch distance in planes
     int chunk = 32;                 // owned planes per block along z
-    int cslot = -1;                 // __constant__ slot holding sp.st[0] (single-type grids)
     SParams sp;
 };
 
 struct MarchArgs {
     int nx, ny, nzl, chunk;
-    int cslot;   // __constant__ slot of the single-type constants (mm_march.cuh: c_sstate)
-    int zmask;   // always 0: keeps the constant loads of the plane loop loop-variant (see ldc2)
+    int pf_dist;  // L2 prefetch distance in planes (k_march VAR & 8)
     const double *x[3];
     double *xo[3];
     const double *v[3];
