@@ -12,7 +12,6 @@ namespace mm {
 
 constexpr int TX = 32;  // lanes along x: one warp per tile row
 constexpr int kStages = 4;   // planes in flight in the staged (bulk-copy) variant
-constexpr int kRowW = 36;    // doubles per staged row (34 used)
 // MM_ABLATE (profiles/ablation.sh only, never in the product build): remove one ingredient of k_march to time the rest.
 // 1 no barriers, 2 no shared-memory exchange (and no barriers), 4 no cell arithmetic, 8 no shuffles, 16 no global stores,
 // 32 no global loads after the first plane.  Results are meaningless; only the launch time is looked at.
@@ -82,9 +81,10 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar) : "memory");
+// one box of a rank-3 tensor map -> shared memory; completion (box bytes, zero fill included) on the mbarrier
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // all states of a cell, Boltzmann-mixed (mmff.py:377-398); the mixing is linear in the gradient, hence in Sq.
@@ -166,13 +166,12 @@ __device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp
 //           of two block-wide barriers per plane; 2 = single-type constants by LDCU inside the loop; 4 = two planes per trip
 //   TY      tile rows (warps per block); the tile owns (TX-2) x (TY-2) node columns
 //
-// Loads (VAR & 2).  With one block of eight warps per SM and one plane of register prefetch, at most 8 x 11 x 256 B are in
-// flight per SM, far below what the HBM latency x bandwidth product asks for: the ablation in profiles/ shows the
-// kernel bound by exactly that (removing the loads saves 0.35 ms of 0.90, removing the cell arithmetic nothing).  The
-// staged variant keeps kStages planes of the tile in flight with bulk asynchronous copies (cp.async.bulk, one per field
-// row and periodic piece, 1-2 per thread, completion counted in bytes on an mbarrier per stage) into shared memory; the
-// threads then read their node with LDS.  A staged row holds the 34 nodes k0-1 .. k0+32 (the copy must start on a
-// 16-byte boundary, the tile starts on an odd node), split in two pieces where it crosses the periodic boundary.
+// Loads (VAR & 2).  The ablation in profiles/ shows where the time of the register-prefetch kernel goes: removing the
+// loads saves 0.35 ms of 0.90, removing the stores 0.22 ms, removing the cell arithmetic nothing - with one block of
+// eight warps per SM the waits do not overlap with anything.  The staged variant keeps kStages planes of the tile in
+// flight with TMA: one tensor-map box (32 x 8 nodes of a padded plane, 2 KB) per field and plane, issued by one thread
+// each, completion counted in bytes on an mbarrier per stage; the threads then read their node with LDS.  (A first
+// version with one cp.async.bulk per field ROW - 88 copies of 256 B per plane - was slower than the register prefetch.)
 //
 // Shared-memory / shuffle traffic per plane and thread (the LSU pipe is as scarce as the FP64 pipe here: measured
 // 1.0 / 2.0 / 2.5 cycles per warp instruction and SM for SHFL / STS.64 / LDS.64, profiles/microbench):
@@ -180,7 +179,8 @@ __device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp
 //   backward  x first, then y, adding rows of equal sign before each exchange: 6 doubles by shuffle, 3 STS + 3 LDS
 template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, int VAR, int TY>
 __global__ void __launch_bounds__(TX *TY, 1)
-k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a, const int write_g) {
+k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a, const __grid_constant__ TmaMaps maps,
+        const int write_g) {
     constexpr int OX = TX - 2, OY = TY - 2;
     constexpr bool PSYNC = (VAR & 1) != 0;   // pairwise named-barrier handshakes instead of block barriers
     constexpr bool TMA = (VAR & 2) != 0;     // node data staged by bulk async copies (NST planes in flight), see below
@@ -190,20 +190,16 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     __shared__ double sf[3][TY][TX];  // forward exchange along y: position of the row above
     __shared__ double sb[3][TY][TX];  // backward exchange along y: x-combined gradient part of the row below
     __shared__ __align__(8) unsigned long long s_full[kStages];
-    extern __shared__ __align__(128) double s_stage[];  // TMA: [kStages][NF][TY][kRowW]
+    extern __shared__ __align__(128) double s_stage[];  // TMA: [kStages][NF][TY][TX]
 
     const int lane = threadIdx.x, row = threadIdx.y;
-    const int nx = a.nx, ny = a.ny;
+    const int nx = a.nx, ny = a.ny, nxp = a.nxp;
+    // thread = node column (k, l) = cell column with that origin vertex; k = -1 and l = -1 are the ghost column / row
+    // of the padded planes, so no tile ever wraps.  Threads beyond the last ghost are clamped onto it (never owned).
     const int k = blockIdx.x * OX + lane - 1, l = blockIdx.y * OY + row - 1;
-    // periodic images along x and y (floor division also handles grids narrower than a tile)
-    const int qx = (k >= 0) ? k / nx : -((-k + nx - 1) / nx);
-    const int qy = (l >= 0) ? l / ny : -((-l + ny - 1) / ny);
-    const int kk = k - qx * nx, ll = l - qy * ny;
+    const int kc = min(k, nx), lc = min(l, ny);
     const bool own_xy = lane >= 1 && lane <= OX && row >= 1 && row <= OY && k < nx && l < ny;
     const StepConsts &sc = *a.sc;
-    const double shx = qx * sc.rv[0] + qy * sc.rv[3];
-    const double shy = qx * sc.rv[1] + qy * sc.rv[4];
-    const double shz = qx * sc.rv[2] + qy * sc.rv[5];
     double R[9], M[9];
     if (ROT) {
 #pragma unroll
@@ -218,10 +214,10 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     const int rowm = (row > 0) ? row - 1 : row;
 
     // 32-bit element indices (the host refuses grids beyond 2^31 padded nodes per array): one IMAD.WIDE per address
-    const unsigned plane = (unsigned)nx * (unsigned)ny;
+    const unsigned plane = (unsigned)nxp * (unsigned)(ny + 2);
     const int c0 = 1 + blockIdx.z * a.chunk;
     const int c1 = min(c0 + a.chunk, a.nzl + 1);
-    unsigned idx = ((unsigned)(c0 - 1) * ny + ll) * nx + kk;  // node (kk, ll) in array plane p
+    unsigned idx = ((unsigned)(c0 - 1) * (ny + 2) + lc + 1) * nxp + kc + 1;  // node (k, l) in array plane p
 
     double acc[14];
 #pragma unroll
@@ -248,49 +244,23 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             nminv_ = a.minv[at];
         }
     };
-    // staged variant: one copy job per thread = (field, tile row, periodic piece); the job's source for plane 0, its
-    // destination inside a stage and its size are fixed for the whole march
+    // staged variant: thread f < NF issues the box of field f (TX x TY nodes of one padded plane) for every staged plane
     const int tid = row * TX + lane;
-    const double *job_src = nullptr;
-    unsigned job_dst = 0, job_bytes = 0;
     unsigned it = 0;  // planes done: plane p = c0 - 1 + it lives in stage it % kStages, barrier phase (it / kStages) & 1
-    constexpr unsigned kStageDoubles = NF * TY * kRowW;
+    constexpr unsigned kStageDoubles = NF * TY * TX;
     if (TMA) {
-        const int ks = blockIdx.x * OX - 2;  // first staged node of a row: even, so every piece starts on 16 bytes
-        const bool wraps = ks < 0 || ks + 34 > nx;
-        const int piece = tid & 1, jrow = (tid >> 1) % TY, f = tid / (2 * TY);
-        if (f < NF) {
-            const int lj = blockIdx.y * OY + jrow - 1;
-            const int qyj = (lj >= 0) ? lj / ny : -((-lj + ny - 1) / ny);
-            const int llj = lj - qyj * ny;
-            int a0 = 0, n = 0, slot = 0;
-            if (piece == 0) {
-                a0 = max(ks, 0);
-                n = min(ks + 34, nx) - a0;
-                slot = a0 - ks;
-            } else if (ks < 0) {  // nodes ks .. -1 are the last nodes of the row
-                a0 = nx + ks;
-                n = -ks;
-            } else if (ks + 34 > nx) {  // nodes nx .. ks+33 are the first nodes of the row
-                n = ks + 34 - nx;
-                slot = nx - ks;
-            }
-            const double *base = f < 3 ? a.x[f] : f < 6 ? a.v[f - 3] : f < 9 ? a.g[f - 6] : f == 9 ? a.m : a.minv;
-            job_src = base + ((size_t)llj * nx + a0);
-            job_dst = smem_u32(s_stage) + (unsigned)(((f * TY + jrow) * kRowW + slot) * 8);
-            job_bytes = (unsigned)n * 8u;
-        }
         if (tid == 0) {
-            for (int st = 0; st < kStages; st++) mbar_init(smem_u32(&s_full[st]), NF * TY * (wraps ? 2 : 1));
+            for (int st = 0; st < kStages; st++) mbar_init(smem_u32(&s_full[st]), NF);
             mbar_fence_init();
         }
         __syncthreads();
     }
-    auto stage_issue = [&](const int q, const unsigned st) {  // plane q -> stage st; every thread with a job arrives + copies
-        if (job_bytes) {
+    auto stage_issue = [&](const int q, const unsigned st) {  // plane q -> stage st
+        if (tid < NF) {
             const unsigned bar = smem_u32(&s_full[st]);
-            mbar_arrive_expect(bar, job_bytes);
-            bulk_g2s(job_dst + st * (kStageDoubles * 8u), job_src + (size_t)q * plane, job_bytes, bar);
+            mbar_arrive_expect(bar, TY * TX * 8u);
+            tma_load_3d(smem_u32(s_stage) + (st * kStageDoubles + tid * (TY * TX)) * 8u, &maps.in[tid], (int)(blockIdx.x * OX),
+                        (int)(blockIdx.y * OY), q, bar);
         }
     };
     if (TMA) {
@@ -309,18 +279,20 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         const unsigned st = it % kStages;
         if (TMA) {
             mbar_wait(smem_u32(&s_full[st]), (it / kStages) & 1u);
-            const double *sp = s_stage + st * kStageDoubles + row * kRowW + lane + 1;  // node k0 + lane = staged slot lane + 1
+            // the box starts at padded column 30 bx, padded row 6 by: thread (lane, row) reads its own slot; slots beyond
+            // the array were filled with zeros (never owned)
+            const double *sp = s_stage + st * kStageDoubles + row * TX + lane;
             cx0 = sp[0];
-            cx1 = sp[TY * kRowW];
-            cx2 = sp[2 * TY * kRowW];
+            cx1 = sp[TY * TX];
+            cx2 = sp[2 * TY * TX];
             if (STEP) {
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                    cv[d] = sp[(3 + d) * TY * kRowW];
-                    cg[d] = sp[(6 + d) * TY * kRowW];
+                    cv[d] = sp[(3 + d) * TY * TX];
+                    cg[d] = sp[(6 + d) * TY * TX];
                 }
-                cm = sp[9 * TY * kRowW];
-                cminv = sp[10 * TY * kRowW];
+                cm = sp[9 * TY * TX];
+                cminv = sp[10 * TY * TX];
             }
         } else {
             cx0 = nx_[0];
@@ -354,7 +326,7 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         }
 
         // ---- node (lane, row, p): true position (and, in STEP mode, kick + drift: verlet.py:144-146) -------------
-        const double xs = cx0 + shx, ys = cx1 + shy, zs = cx2 + shz;
+        const double xs = cx0, ys = cx1, zs = cx2;  // ghosts already carry their periodic shift
         double r[3];
         if (ROT) {
 #pragma unroll

@@ -21,6 +21,7 @@
 // Apron cells are recomputed by neighbouring blocks (tile 32 x TY threads -> 30 x (TY-2) owned nodes): the price of
 // never materialising per-cell data.  DESIGN.md discusses the trade-off and the measured numbers.  The kernel itself
 // lives in mm_march.cuh; this file holds the layout conversions, halo planes and the launch logic.
+#include <cstring>
 #include <vector>
 
 #include "mm_internal.h"
@@ -30,12 +31,41 @@
 namespace mm {
 
 // ---------------------------------------------------------------------------------------------------------------
-// halo planes: p = 0 <- p = nzl (minus c), p = nzl + 1 <- p = 1 (plus c); c = third domain vector of the stored frame
+// Ghost nodes.  Every array is padded by one node on each side of all three axes (mm_structured.cuh): a tile of the
+// marching kernel then never crosses a periodic boundary - the ghosts hold the periodic images, positions already shifted
+// by the domain vectors of the STORED frame (a, b along x / y here; c along z below).
+//   pass 1 (k_halo_xy): x / y ghosts of the owned planes 1 .. nzl, corners included (source = wrapped node, shift qx a + qy b)
+//   pass 2 (k_halo):    whole padded planes  p = 0 <- p = nzl (minus c),  p = nzl + 1 <- p = 1 (plus c)
 struct HaloArgs {
     double *f[9];
     int nfields;
     int npos;  // the first npos fields are position components 0, 1, 2
 };
+
+__global__ void __launch_bounds__(256)
+k_halo_xy(const __grid_constant__ HaloArgs h, int nx, int ny, int nxp, int64_t plane, int nzl, const StepConsts *sc) {
+    const int per_plane = 2 * (nx + 2) + 2 * ny;  // two full ghost rows (with corners) + two ghost columns
+    const int64_t total = (int64_t)per_plane * nzl;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = 1 + (int)(i / per_plane);
+        int j = (int)(i % per_plane), k, l;
+        if (j < 2 * (nx + 2)) {
+            l = (j < nx + 2) ? -1 : ny;
+            k = (j % (nx + 2)) - 1;
+        } else {
+            j -= 2 * (nx + 2);
+            k = (j < ny) ? -1 : nx;
+            l = j % ny;
+        }
+        const int qx = (k < 0) ? -1 : (k >= nx ? 1 : 0), qy = (l < 0) ? -1 : (l >= ny ? 1 : 0);
+        const int64_t dst = ((int64_t)p * (ny + 2) + l + 1) * nxp + k + 1;
+        const int64_t src = ((int64_t)p * (ny + 2) + (l - qy * ny) + 1) * nxp + (k - qx * nx) + 1;
+        for (int f = 0; f < h.nfields; f++) {
+            const double shift = (f < h.npos) ? qx * sc->rv[f] + qy * sc->rv[3 + f] : 0.0;
+            h.f[f][dst] = h.f[f][src] + shift;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256)
 k_halo(const __grid_constant__ HaloArgs h, int64_t plane, int nzl, const StepConsts *sc) {
@@ -45,6 +75,27 @@ k_halo(const __grid_constant__ HaloArgs h, int64_t plane, int nzl, const StepCon
             h.f[f][i] = h.f[f][(int64_t)nzl * plane + i] - c;
             h.f[f][(int64_t)(nzl + 1) * plane + i] = h.f[f][plane + i] + c;
         }
+    }
+}
+
+// cell types: the same two passes on bytes
+__global__ void __launch_bounds__(256)
+k_halo_xy_u8(uint8_t *f, int nx, int ny, int nxp, int nzl) {
+    const int per_plane = 2 * (nx + 2) + 2 * ny;
+    const int64_t total = (int64_t)per_plane * nzl;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = 1 + (int)(i / per_plane);
+        int j = (int)(i % per_plane), k, l;
+        if (j < 2 * (nx + 2)) {
+            l = (j < nx + 2) ? -1 : ny;
+            k = (j % (nx + 2)) - 1;
+        } else {
+            j -= 2 * (nx + 2);
+            k = (j < ny) ? -1 : nx;
+            l = j % ny;
+        }
+        const int ks = (k < 0) ? nx - 1 : (k >= nx ? 0 : k), ls = (l < 0) ? ny - 1 : (l >= ny ? 0 : l);
+        f[((int64_t)p * (ny + 2) + l + 1) * nxp + k + 1] = f[((int64_t)p * (ny + 2) + ls + 1) * nxp + ks + 1];
     }
 }
 
@@ -62,7 +113,7 @@ k_halo_u8(uint8_t *f, int64_t plane, int nzl) {
 constexpr int TT = 32;
 
 __global__ void __launch_bounds__(TT * 8)
-k_aos_to_soa(const double *__restrict__ aos, double *s0, double *s1, double *s2, int nx, int ny, int nz) {
+k_aos_to_soa(const double *__restrict__ aos, double *s0, double *s1, double *s2, int nx, int ny, int nz, int nxp) {
     __shared__ double tile[3][TT][TT + 1];  // [d][k][m]
     const int k0 = blockIdx.x * TT, l = blockIdx.y, m0 = blockIdx.z * TT;
     const int mt = min(TT, nz - m0), kt = min(TT, nx - k0);
@@ -76,7 +127,7 @@ k_aos_to_soa(const double *__restrict__ aos, double *s0, double *s1, double *s2,
     const int kk = threadIdx.x;
     for (int mm = threadIdx.y; mm < mt; mm += 8) {
         if (kk < kt) {
-            const int64_t at = ((int64_t)(m0 + mm + 1) * ny + l) * nx + k0 + kk;  // +1: skip the lower halo plane
+            const int64_t at = ((int64_t)(m0 + mm + 1) * (ny + 2) + l + 1) * nxp + k0 + kk + 1;  // +1: skip the ghosts
 #pragma unroll
             for (int d = 0; d < 3; d++) dst[d][at] = tile[d][kk][mm];
         }
@@ -85,7 +136,7 @@ k_aos_to_soa(const double *__restrict__ aos, double *s0, double *s1, double *s2,
 
 __global__ void __launch_bounds__(TT * 8)
 k_soa_to_aos(const double *__restrict__ s0, const double *__restrict__ s1, const double *__restrict__ s2, double *aos,
-             int nx, int ny, int nz) {
+             int nx, int ny, int nz, int nxp) {
     __shared__ double tile[3][TT][TT + 1];  // [d][k][m]
     const int k0 = blockIdx.x * TT, l = blockIdx.y, m0 = blockIdx.z * TT;
     const int mt = min(TT, nz - m0), kt = min(TT, nx - k0);
@@ -94,7 +145,7 @@ k_soa_to_aos(const double *__restrict__ s0, const double *__restrict__ s1, const
     const int kk = threadIdx.x;
     for (int mm = threadIdx.y; mm < mt; mm += 8) {
         if (kk < kt) {
-            const int64_t at = ((int64_t)(m0 + mm + 1) * ny + l) * nx + k0 + kk;
+            const int64_t at = ((int64_t)(m0 + mm + 1) * (ny + 2) + l + 1) * nxp + k0 + kk + 1;
 #pragma unroll
             for (int d = 0; d < 3; d++) tile[d][kk][mm] = src[d][at];
         }
@@ -107,22 +158,23 @@ k_soa_to_aos(const double *__restrict__ s0, const double *__restrict__ s1, const
 }
 
 __global__ void __launch_bounds__(256)
-k_mass_to_soa(const double *__restrict__ masses, double *m, double *minv, int nx, int ny, int nz) {
+k_mass_to_soa(const double *__restrict__ masses, double *m, double *minv, int nx, int ny, int nz, int nxp) {
     const int64_t n = (int64_t)nx * ny * nz;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)(i % nx), l = (int)((i / nx) % ny), mm_ = (int)(i / ((int64_t)nx * ny));
         const double v = masses[((int64_t)k * ny + l) * nz + mm_];
-        m[i + (int64_t)nx * ny] = v;
-        minv[i + (int64_t)nx * ny] = 1.0 / v;
+        const int64_t at = ((int64_t)(mm_ + 1) * (ny + 2) + l + 1) * nxp + k + 1;
+        m[at] = v;
+        minv[at] = 1.0 / v;
     }
 }
 
 __global__ void __launch_bounds__(256)
-k_type_to_soa(const uint8_t *__restrict__ info, uint8_t *type, int nx, int ny, int nz) {
+k_type_to_soa(const uint8_t *__restrict__ info, uint8_t *type, int nx, int ny, int nz, int nxp) {
     const int64_t n = (int64_t)nx * ny * nz;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)(i % nx), l = (int)((i / nx) % ny), m = (int)(i / ((int64_t)nx * ny));
-        type[i + (int64_t)nx * ny] = info[((int64_t)k * ny + l) * nz + m] & 15u;
+        type[((int64_t)(m + 1) * (ny + 2) + l + 1) * nxp + k + 1] = info[((int64_t)k * ny + l) * nz + m] & 15u;
     }
 }
 
@@ -192,6 +244,39 @@ static void fold_sparams(const KParams &kp, SParams &sp) {
     }
 }
 
+// TMA descriptors of the padded SoA arrays (rank 3: x fastest, then y, then z; box = one tile of one plane).  The encoder
+// lives in the driver library; it is reached through the runtime (cudaGetDriverEntryPoint), so nothing links to libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int sg_encode_maps(mm_handle *h) {
+    SGrid &g = h->sg;
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            return MM_ERR_CUDA;
+        }
+        encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)g.nxp, (cuuint64_t)(g.ny + 2), (cuuint64_t)(g.nzl + 3)};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.nxp * 8, (cuuint64_t)g.plane * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)TX, (cuuint32_t)g.tile_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    auto one = [&](CUtensorMap *m, double *p) {
+        return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    bool ok = true;
+    for (int c = 0; c < 2; c++)
+        for (int d = 0; d < 3; d++) ok = ok && one(&g.tm_x[c][d], g.x[c][d]) && one(&g.tm_v[c][d], g.v[c][d]) && one(&g.tm_g[c][d], g.g[c][d]);
+    ok = ok && one(&g.tm_m, g.m) && one(&g.tm_minv, g.minv);
+    return ok ? MM_OK : MM_ERR_CUDA;
+}
+
 bool sg_eligible(const mm_handle *h) {
     return h->structured && h->model == MM_MODEL_ORIGINAL && h->nx >= 2 && h->ny >= 2 && h->nz >= 2;
 }
@@ -211,7 +296,8 @@ int sg_setup(mm_handle *h) {
     // The reference enumerates id = (k*ny + l)*nz + m with k along the FIRST domain vector.  Device planes are indexed
     // (x = k fastest, y = l, z = m slowest): the marching direction is the reference's third axis, the lanes run along
     // its first axis.
-    g.plane = (int64_t)g.nx * g.ny;
+    g.nxp = (g.nx + 2 + 1) & ~1;  // one ghost node on each side; even pitch (16-byte rows for the bulk-copy engine)
+    g.plane = (int64_t)g.nxp * (g.ny + 2);
     g.npad = g.plane * (g.nzl + 3);  // two halo planes + one spare plane for the prefetch of the marching kernel
     fold_sparams(h->kp, g.sp);
     const size_t bytes = sizeof(double) * g.npad;
@@ -229,6 +315,7 @@ int sg_setup(mm_handle *h) {
     MM_CUDA(cudaMemsetAsync(g.m, 0, bytes, h->stream));
     MM_CUDA(cudaMemsetAsync(g.minv, 0, bytes, h->stream));
     MM_CUDA(cudaMalloc(&g.type, g.npad));
+    g.tma_ok = sg_encode_maps(h) == MM_OK ? 1 : 0;
     MM_CUDA(cudaMalloc(&g.d_sc, sizeof(StepConsts)));
     MM_CUDA(cudaMalloc(&g.d_sp, sizeof(SParams)));
     MM_CUDA(cudaMemcpyAsync(g.d_sp, &g.sp, sizeof(SParams), cudaMemcpyHostToDevice, h->stream));
@@ -241,7 +328,9 @@ int sg_setup(mm_handle *h) {
     g.nblocks = sg_blocks(h, grid);
     g.nblocks_alloc = g.nblocks;
     MM_CUDA(cudaMalloc(&g.d_partials, sizeof(double) * (size_t)g.nblocks * kRedSlots));
-    k_type_to_soa<<<grid_for(h, h->ncells, 256), 256, 0, h->stream>>>(h->d_cell_info, g.type, g.nx, g.ny, g.nzl);
+    MM_CUDA(cudaMemsetAsync(g.type, 0, g.npad, h->stream));
+    k_type_to_soa<<<grid_for(h, h->ncells, 256), 256, 0, h->stream>>>(h->d_cell_info, g.type, g.nx, g.ny, g.nzl, g.nxp);
+    k_halo_xy_u8<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * g.nzl, 256), 256, 0, h->stream>>>(g.type, g.nx, g.ny, g.nxp, g.nzl);
     if (h->slab_count <= 1)  // slabs receive the neighbours' boundary types in mm_comm_init
         k_halo_u8<<<grid_for(h, g.plane, 256), 256, 0, h->stream>>>(g.type, g.plane, g.nzl);
     MM_CUDA(cudaGetLastError());
@@ -295,7 +384,9 @@ int sg_halo(mm_handle *h, bool pos, bool vel, bool grad) {
     if (grad)
         for (int d = 0; d < 3; d++) ha.f[ha.nfields++] = g.g[g.cg][d];
     if (ha.nfields == 0) return MM_OK;
-    if (h->slab_count > 1) return comm_halo(h, ha.f, ha.nfields, ha.npos);  // planes travel between the slabs
+    k_halo_xy<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * g.nzl, 256), 256, 0, h->stream>>>(ha, g.nx, g.ny, g.nxp, g.plane, g.nzl, g.d_sc);
+    h->launches++;
+    if (h->slab_count > 1) return comm_halo(h, ha.f, ha.nfields, ha.npos);  // (padded) planes travel between the slabs
     k_halo<<<grid_for(h, g.plane, 256), 256, 0, h->stream>>>(ha, g.plane, g.nzl, g.d_sc);
     h->launches++;
     return MM_OK;
@@ -308,6 +399,8 @@ int sg_halo_mass(mm_handle *h) {
     ha.npos = 0;
     ha.f[0] = g.m;
     ha.f[1] = g.minv;
+    k_halo_xy<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * g.nzl, 256), 256, 0, h->stream>>>(ha, g.nx, g.ny, g.nxp, g.plane, g.nzl, g.d_sc);
+    h->launches++;
     if (h->slab_count > 1) return comm_halo(h, ha.f, 2, 0);
     k_halo<<<grid_for(h, g.plane, 256), 256, 0, h->stream>>>(ha, g.plane, g.nzl, g.d_sc);
     h->launches++;
@@ -318,21 +411,21 @@ static dim3 transpose_grid(const SGrid &g) { return dim3((g.nx + TT - 1) / TT, g
 
 int sg_pos_from_aos(mm_handle *h, const double *d_aos) {
     SGrid &g = h->sg;
-    k_aos_to_soa<<<transpose_grid(g), dim3(TT, 8), 0, h->stream>>>(d_aos, g.x[g.cx][0], g.x[g.cx][1], g.x[g.cx][2], g.nx, g.ny, g.nzl);
+    k_aos_to_soa<<<transpose_grid(g), dim3(TT, 8), 0, h->stream>>>(d_aos, g.x[g.cx][0], g.x[g.cx][1], g.x[g.cx][2], g.nx, g.ny, g.nzl, g.nxp);
     h->launches++;
     return sg_halo(h, true, false, false);
 }
 
 int sg_vel_from_aos(mm_handle *h, const double *d_aos) {
     SGrid &g = h->sg;
-    k_aos_to_soa<<<transpose_grid(g), dim3(TT, 8), 0, h->stream>>>(d_aos, g.v[g.cv][0], g.v[g.cv][1], g.v[g.cv][2], g.nx, g.ny, g.nzl);
+    k_aos_to_soa<<<transpose_grid(g), dim3(TT, 8), 0, h->stream>>>(d_aos, g.v[g.cv][0], g.v[g.cv][1], g.v[g.cv][2], g.nx, g.ny, g.nzl, g.nxp);
     h->launches++;
     return sg_halo(h, false, true, false);
 }
 
 int sg_mass_from_aos(mm_handle *h, const double *d_masses) {
     SGrid &g = h->sg;
-    k_mass_to_soa<<<grid_for(h, h->nnodes, 256), 256, 0, h->stream>>>(d_masses, g.m, g.minv, g.nx, g.ny, g.nzl);
+    k_mass_to_soa<<<grid_for(h, h->nnodes, 256), 256, 0, h->stream>>>(d_masses, g.m, g.minv, g.nx, g.ny, g.nzl, g.nxp);
     h->launches++;
     return sg_halo_mass(h);
 }
@@ -340,7 +433,7 @@ int sg_mass_from_aos(mm_handle *h, const double *d_masses) {
 int sg_to_aos(mm_handle *h, int which, double *d_aos) {  // 0 pos, 1 vel, 2 gpos
     SGrid &g = h->sg;
     double **src = which == 0 ? g.x[g.cx] : which == 1 ? g.v[g.cv] : g.g[g.cg];
-    k_soa_to_aos<<<transpose_grid(g), dim3(TT, 8), 0, h->stream>>>(src[0], src[1], src[2], d_aos, g.nx, g.ny, g.nzl);
+    k_soa_to_aos<<<transpose_grid(g), dim3(TT, 8), 0, h->stream>>>(src[0], src[1], src[2], d_aos, g.nx, g.ny, g.nzl, g.nxp);
     h->launches++;
     return MM_OK;
 }
@@ -350,6 +443,7 @@ static void fill_args(mm_handle *h, MarchArgs &a) {
     a.nx = g.nx;
     a.ny = g.ny;
     a.nzl = g.nzl;
+    a.nxp = g.nxp;
     a.chunk = g.chunk;
     a.pf_dist = g.pf_dist;
     for (int d = 0; d < 3; d++) {
@@ -373,7 +467,7 @@ static int launch_one(mm_handle *h, const MarchArgs &a, int write_g) {
     sg_blocks(h, grid);
     prof_begin(h, STEP);
     // staged variant: kStages planes of the tile in dynamic shared memory (opt-in above 48 KB, once per instantiation)
-    constexpr size_t dyn = (VAR & 2) ? sizeof(double) * kStages * (STEP ? 11 : 3) * TY * kRowW : 0;
+    constexpr size_t dyn = (VAR & 2) ? sizeof(double) * kStages * (STEP ? 11 : 3) * TY * TX : 0;
     if (dyn > 0) {
         static bool configured[64] = {false};
         if (!configured[h->device & 63]) {
@@ -381,7 +475,20 @@ static int launch_one(mm_handle *h, const MarchArgs &a, int write_g) {
             configured[h->device & 63] = true;
         }
     }
-    k_march<STEP, SINGLE, ROT, VM, LEAN, VAR, TY><<<grid, dim3(TX, TY), dyn, h->stream>>>(h->sg.sp, a, write_g);
+    TmaMaps maps;
+    if (VAR & 2) {
+        const SGrid &g = h->sg;
+        for (int d = 0; d < 3; d++) {
+            maps.in[d] = g.tm_x[g.cx][d];
+            maps.in[3 + d] = g.tm_v[g.cv][d];
+            maps.in[6 + d] = g.tm_g[g.cg][d];
+        }
+        maps.in[9] = g.tm_m;
+        maps.in[10] = g.tm_minv;
+    } else {
+        memset(&maps, 0, sizeof(maps));
+    }
+    k_march<STEP, SINGLE, ROT, VM, LEAN, VAR, TY><<<grid, dim3(TX, TY), dyn, h->stream>>>(h->sg.sp, a, maps, write_g);
     prof_end(h);
     h->launches++;
     MM_CUDA(cudaGetLastError());
@@ -408,8 +515,7 @@ static int launch_sel(mm_handle *h, const MarchArgs &a, bool step, int rot, int 
 static int launch_march(mm_handle *h, const MarchArgs &a, bool step, int rot, int vm, bool lean, int write_g) {
     const bool single = h->sg.sp.ntypes == 1 && h->sg.sp.nstates[0] == 1;
     if (!single) return launch_sel<false, 0>(h, a, step, rot, vm, false, write_g);
-    // staged loads need 16-byte aligned row pieces (nx even) and at most one periodic crossing per staged row
-    const bool stageable = h->sg.nx % 2 == 0 && h->sg.nx >= 64;
+    const bool stageable = h->sg.tma_ok != 0;  // tensor maps encoded (sg_setup)
     int var = h->sg.variant & 15;
     if (!stageable) var &= ~2;
     if (var & 2) var &= ~1;  // the refill of a stage relies on the block barrier

@@ -1,5 +1,6 @@
 // mm_structured.cuh - data structures of the structured-grid (full periodic nx x ny x nz) fast path
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -35,19 +36,24 @@ struct StepConsts {
     double pad[3];
 };
 
-// SoA planes in z-major order with one halo plane below and above the nzl owned planes:
-//   index(k, l, p) = (p * ny + l) * nx + k,   p = 0 (lower halo), 1..nzl (owned), nzl + 1 (upper halo)
-// so that a z-slab of a multi-GPU decomposition is one contiguous range and its halos are whole planes.
+// SoA planes in z-major order, padded by one ghost node on each side of every axis (periodic images, kept current by
+// sg_halo; positions of ghosts already carry the domain-vector shift):
+//   index(k, l, p) = (p * (ny + 2) + l + 1) * nxp + k + 1,   k = -1 .. nx, l = -1 .. ny, p = 0 (lower halo), 1..nzl (owned),
+//   nzl + 1 (upper halo); nxp = nx + 2 rounded up to an even pitch.  A z-slab of a multi-GPU decomposition is one contiguous
+// range of planes and its halos are whole (padded) planes; a tile of the marching kernel never wraps.
 struct SGrid {
     int active = 0;
     int nx = 0, ny = 0, nzl = 0;
-    int64_t plane = 0, npad = 0;
+    int nxp = 0;                    // row pitch in nodes
+    int64_t plane = 0, npad = 0;    // padded plane (nxp * (ny + 2)) and array size in nodes
     double *x[2][3] = {{nullptr}};  // ping-pong: kernels that move nodes read one set and write the other
     double *v[2][3] = {{nullptr}};
     double *g[2][3] = {{nullptr}};
     double *m = nullptr, *minv = nullptr;
     uint8_t *type = nullptr;
     int cx = 0, cv = 0, cg = 0;     // which copy is current
+    CUtensorMap tm_x[2][3], tm_v[2][3], tm_g[2][3], tm_m, tm_minv;  // load descriptors of the arrays above
+    int tma_ok = 0;                 // descriptors encoded (driver entry point available, pitch constraints met)
     StepConsts *d_sc = nullptr;
     SParams *d_sp = nullptr;        // device copy of sp
     StepConsts *h_sc = nullptr;     // pinned staging
@@ -60,8 +66,15 @@ struct SGrid {
     SParams sp;
 };
 
+// Tensor maps (TMA descriptors) of the arrays one launch of the staged kernel variant reads: box = TX x TY x 1 nodes of a
+// padded plane; coordinates outside the array read as zero (the partial tiles at the upper x / y edge)
+struct alignas(64) TmaMaps {
+    CUtensorMap in[11];  // x0 x1 x2 v0 v1 v2 g0 g1 g2 m 1/m
+};
+
 struct MarchArgs {
     int nx, ny, nzl, chunk;
+    int nxp;      // row pitch of the padded planes
     int pf_dist;  // L2 prefetch distance in planes (k_march VAR & 8)
     const double *x[3];
     double *xo[3];
