@@ -45,8 +45,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tile-rows", type=int, default=0, help="tuning: warps per block of the marching kernel (8/12/16)")
-    ap.add_argument("--variant", type=int, default=-1, help="tuning bits of the marching kernel (1 pairwise barriers, 2 LDCU constants, 4 two planes per trip)")
-    ap.add_argument("--pf-dist", type=int, default=0, help="tuning: L2 prefetch distance in planes (variant bit 8)")
+    ap.add_argument("--variant", type=int, default=-1, help="tuning bits of the marching kernel (1 pairwise barriers, 2 TMA loads, 4 two planes per trip, 8 TMA stores)")
     ap.add_argument("--chunk", type=int, default=0, help="tuning: planes per block along z")
     ap.add_argument("--generic", action="store_true", help="force the indexed-topology kernels (no structured path)")
     return ap.parse_args()
@@ -218,8 +217,6 @@ def main():
         part = ForcePartMechanical(system, model=args.model, device=local_rank, slab=layout.slab_arg())
     if args.tile_rows:
         _lib.check(lib.mm_set_option(part.handle, b"tile_rows", args.tile_rows))
-    if args.pf_dist:
-        _lib.check(lib.mm_set_option(part.handle, b"pf_dist", args.pf_dist))
     if args.chunk:
         _lib.check(lib.mm_set_option(part.handle, b"chunk", args.chunk))
     if args.variant >= 0:

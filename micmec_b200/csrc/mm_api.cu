@@ -374,10 +374,6 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value) {
         h->sg.active = 1;
         return MM_OK;
     }
-    if (strcmp(name, "pf_dist") == 0) {
-        h->sg.pf_dist = (int)value < 1 ? 1 : (int)value;
-        return MM_OK;
-    }
     if (strcmp(name, "variant") == 0) {
         h->sg.variant = (int)value & 15;
         return MM_OK;

@@ -12,6 +12,7 @@ namespace mm {
 
 constexpr int TX = 32;  // lanes along x: one warp per tile row
 constexpr int kStages = 4;   // planes in flight in the staged (bulk-copy) variant
+constexpr int kOutField = 192;  // doubles per field of the output staging tile (30 x 6 owned nodes = 180, padded to 128-byte multiples)
 // MM_ABLATE (profiles/ablation.sh only, never in the product build): remove one ingredient of k_march to time the rest.
 // 1 no barriers, 2 no shared-memory exchange (and no barriers), 4 no cell arithmetic, 8 no shuffles, 16 no global stores,
 // 32 no global loads after the first plane.  Results are meaningless; only the launch time is looked at.
@@ -86,6 +87,17 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
                  "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+
+// shared memory -> one box of a rank-3 tensor map (bulk-group completion); parts of the box outside the array are dropped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int c0, int c1, int c2, unsigned src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<unsigned long long>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (executed by the writers before the barrier)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // all states of a cell, Boltzmann-mixed (mmff.py:377-398); the mixing is linear in the gradient, hence in Sq.
 template <bool SINGLE, bool WANT_VIR>
@@ -163,7 +175,8 @@ __device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp
 //   VM      STEP only: pending velocity transform  0 none, 1 scalar (Mvel[0]), 2 full 3x3
 //   LEAN    no virial, kinetic-energy diagonal only (NVE / NVT steps whose pressure nobody looks at)
 //   VAR     tuning bits (measured in profiles/): 1 = neighbouring rows synchronise pairwise through named barriers instead
-//           of two block-wide barriers per plane; 2 = single-type constants by LDCU inside the loop; 4 = two planes per trip
+//           of two block-wide barriers per plane; 2 = TMA loads (kStages planes in flight); 4 = two planes per trip;
+//           8 = with 2: TMA stores through a shared-memory tile
 //   TY      tile rows (warps per block); the tile owns (TX-2) x (TY-2) node columns
 //
 // Loads (VAR & 2).  The ablation in profiles/ shows where the time of the register-prefetch kernel goes: removing the
@@ -185,12 +198,12 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     constexpr bool PSYNC = (VAR & 1) != 0;   // pairwise named-barrier handshakes instead of block barriers
     constexpr bool TMA = (VAR & 2) != 0;     // node data staged by bulk async copies (NST planes in flight), see below
     constexpr int UNR = (VAR & 4) ? 2 : 1;   // planes per loop trip
-    constexpr bool PF2 = (VAR & 8) != 0;     // prefetch plane p + pf_dist into L2
+    constexpr bool TST = TMA && (VAR & 8) != 0;  // results leave through a shared-memory tile and TMA stores (measured slower)
     constexpr int NF = STEP ? 11 : 3;        // staged fields per node: x (3) [, v (3), g (3), m, 1/m]
     __shared__ double sf[3][TY][TX];  // forward exchange along y: position of the row above
     __shared__ double sb[3][TY][TX];  // backward exchange along y: x-combined gradient part of the row below
     __shared__ __align__(8) unsigned long long s_full[kStages];
-    extern __shared__ __align__(128) double s_stage[];  // TMA: [kStages][NF][TY][TX]
+    extern __shared__ __align__(128) double s_stage[];  // TMA: [kStages][NF][TY][kBoxW], then the output tiles [2][9][kOutField]
 
     const int lane = threadIdx.x, row = threadIdx.y;
     const int nx = a.nx, ny = a.ny, nxp = a.nxp;
@@ -217,7 +230,7 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     const unsigned plane = (unsigned)nxp * (unsigned)(ny + 2);
     const int c0 = 1 + blockIdx.z * a.chunk;
     const int c1 = min(c0 + a.chunk, a.nzl + 1);
-    unsigned idx = ((unsigned)(c0 - 1) * (ny + 2) + lc + 1) * nxp + kc + 1;  // node (k, l) in array plane p
+    unsigned idx = ((unsigned)(c0 - 1) * (ny + 2) + lc + 1) * nxp + kc + kGhostX;  // node (k, l) in array plane p
 
     double acc[14];
 #pragma unroll
@@ -247,7 +260,12 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     // staged variant: thread f < NF issues the box of field f (TX x TY nodes of one padded plane) for every staged plane
     const int tid = row * TX + lane;
     unsigned it = 0;  // planes done: plane p = c0 - 1 + it lives in stage it % kStages, barrier phase (it / kStages) & 1
-    constexpr unsigned kStageDoubles = NF * TY * TX;
+    constexpr unsigned kStageDoubles = NF * TY * kBoxW;
+    // output tile (staged variant): the owned 30 x 6 nodes of a plane, dense rows of 30 (the box of the store descriptors),
+    // two copies by plane parity.  The threads of the owned lanes / rows write their node, the async proxy stores the box.
+    double *const s_out = s_stage + kStages * kStageDoubles;
+    const bool in_box = lane >= 1 && lane <= OX && row >= 1 && row <= OY;
+    const int oslot = (row - 1) * OX + (lane - 1);
     if (TMA) {
         if (tid == 0) {
             for (int st = 0; st < kStages; st++) mbar_init(smem_u32(&s_full[st]), NF);
@@ -258,8 +276,9 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     auto stage_issue = [&](const int q, const unsigned st) {  // plane q -> stage st
         if (tid < NF) {
             const unsigned bar = smem_u32(&s_full[st]);
-            mbar_arrive_expect(bar, TY * TX * 8u);
-            tma_load_3d(smem_u32(s_stage) + (st * kStageDoubles + tid * (TY * TX)) * 8u, &maps.in[tid], (int)(blockIdx.x * OX),
+            mbar_arrive_expect(bar, TY * kBoxW * 8u);
+            // node k0 - 1 of the tile is padded column 30 bx + 1; the box starts one column earlier (even)
+            tma_load_3d(smem_u32(s_stage) + (st * kStageDoubles + tid * (TY * kBoxW)) * 8u, &maps.in[tid], (int)(blockIdx.x * OX),
                         (int)(blockIdx.y * OY), q, bar);
         }
     };
@@ -278,21 +297,21 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         double cx0, cx1, cx2, cv[3] = {0, 0, 0}, cg[3] = {0, 0, 0}, cm = 0.0, cminv = 0.0;
         const unsigned st = it % kStages;
         if (TMA) {
-            mbar_wait(smem_u32(&s_full[st]), (it / kStages) & 1u);
-            // the box starts at padded column 30 bx, padded row 6 by: thread (lane, row) reads its own slot; slots beyond
-            // the array were filled with zeros (never owned)
-            const double *sp = s_stage + st * kStageDoubles + row * TX + lane;
+            if (!(MM_ABLATE & 32) || it < kStages) mbar_wait(smem_u32(&s_full[st]), (it / kStages) & 1u);
+            // the box starts at padded column 30 bx, padded row 6 by: thread (lane, row) reads slot (lane + 1, row); slots
+            // beyond the array were filled with zeros (never owned)
+            const double *sp = s_stage + st * kStageDoubles + row * kBoxW + lane + 1;
             cx0 = sp[0];
-            cx1 = sp[TY * TX];
-            cx2 = sp[2 * TY * TX];
+            cx1 = sp[TY * kBoxW];
+            cx2 = sp[2 * TY * kBoxW];
             if (STEP) {
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                    cv[d] = sp[(3 + d) * TY * TX];
-                    cg[d] = sp[(6 + d) * TY * TX];
+                    cv[d] = sp[(3 + d) * TY * kBoxW];
+                    cg[d] = sp[(6 + d) * TY * kBoxW];
                 }
-                cm = sp[9 * TY * TX];
-                cminv = sp[10 * TY * TX];
+                cm = sp[9 * TY * kBoxW];
+                cminv = sp[10 * TY * kBoxW];
             }
         } else {
             cx0 = nx_[0];
@@ -308,21 +327,6 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
                 }
             }
             if (!(MM_ABLATE & 32)) issue_loads(idx + plane);
-            if (PF2 && p + a.pf_dist <= c1) {  // every lane: the L2 fills sectors (32 B), not lines
-                const unsigned at = idx + a.pf_dist * plane;
-#pragma unroll
-                for (int d = 0; d < 3; d++) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x[d] + at));
-                    if (STEP) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.v[d] + at));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.g[d] + at));
-                    }
-                }
-                if (STEP) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.m + at));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.minv + at));
-                }
-            }
         }
 
         // ---- node (lane, row, p): true position (and, in STEP mode, kick + drift: verlet.py:144-146) -------------
@@ -349,11 +353,19 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
                 r[j] = fma(dt, vcur[j], r[j]);
             }
         }
-        if ((STEP || ROT == 2) && CELL) {  // owned columns carry no periodic shift
-            const bool px = own_xy && p < c1;
+        if ((STEP || ROT == 2) && CELL) {
+            if (TST) {
+                if (in_box) {
 #pragma unroll
-            for (int j = 0; j < 3; j++) st_if(px, a.xo[j] + idx, r[j]);
+                    for (int j = 0; j < 3; j++) s_out[((p & 1) * 9 + j) * kOutField + oslot] = r[j];
+                }
+            } else {
+                const bool px = own_xy && p < c1;
+#pragma unroll
+                for (int j = 0; j < 3; j++) st_if(px, a.xo[j] + idx, r[j]);
+            }
         }
+        if (TST) fence_async_smem();  // the tile parts written since the last barrier (x of plane p; v, g of plane p-2)
 
         // ---- forward butterfly: y through shared memory, x by shuffle, z in registers -------------------------------
 #pragma unroll
@@ -366,7 +378,21 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         } else {
             __syncthreads();
         }
-        if (TMA && p + kStages <= c1) stage_issue(p + kStages, st);  // every thread has read stage st before the barrier
+        if (TMA && !(MM_ABLATE & 32) && p + kStages <= c1) stage_issue(p + kStages, st);  // all threads have read stage st
+        if (TST) {  // warp 1 stores: x of plane p (tile p & 1), v and g of node plane p-2 (written at the end of iteration p-1)
+            const int f = tid - TX;
+            if (f >= 0 && f < 9) {
+                const bool xs_ok = (STEP || ROT == 2) && CELL && p < c1;
+                const bool vg_ok = p >= c0 + 2 && (f < 6 ? STEP != 0 : write_g != 0);
+                if (f < 3 ? xs_ok : vg_ok) {
+                    const int q = f < 3 ? p : p - 2;
+                    tma_store_3d(&maps.out[f], (int)(blockIdx.x * OX) + kGhostX, (int)(blockIdx.y * OY) + 1, q,
+                                 smem_u32(s_out + (((f < 3 ? p : p - 1) & 1) * 9 + f) * kOutField));
+                }
+                tma_store_commit();
+                tma_store_wait_read<1>();  // the group of iteration p-1 has read its tile: safe to rewrite after the next barrier
+            }
+        }
         double pxy[3], dxy[3], pyd[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
@@ -449,7 +475,11 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
                     vn[j] = fma(-hminv_prev, g[j], vh[j]);
-                    st_if(own_xy, a.vo[j] + at, vn[j]);
+                    if (TST) {
+                        if (in_box) s_out[((p & 1) * 9 + 3 + j) * kOutField + oslot] = vn[j];
+                    } else {
+                        st_if(own_xy, a.vo[j] + at, vn[j]);
+                    }
                 }
                 const double mo = own_xy ? mprev : 0.0;
                 const double mx = mo * vn[0], my = mo * vn[1], mz = mo * vn[2];
@@ -462,9 +492,16 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
                     acc[12] = fma(mx, vn[1], acc[12]);
                 }
             }
-            const bool pg = own_xy && write_g;
+            if (TST) {
+                if (in_box) {
 #pragma unroll
-            for (int j = 0; j < 3; j++) st_if(pg, a.go[j] + at, g[j]);
+                    for (int j = 0; j < 3; j++) s_out[((p & 1) * 9 + 6 + j) * kOutField + oslot] = g[j];
+                }
+            } else {
+                const bool pg = own_xy && write_g;
+#pragma unroll
+                for (int j = 0; j < 3; j++) st_if(pg, a.go[j] + at, g[j]);
+            }
             if (!LEAN) acc[13] += own_xy ? fma(g[0], g[0], fma(g[1], g[1], g[2] * g[2])) : 0.0;
         }
         if (CELL) {
@@ -487,6 +524,18 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
 #pragma unroll UNR
     for (int p = c0 + 1; p <= c1; p++) plane_body(std::true_type{}, std::true_type{}, p);
 
+    if (TST) {  // drain: v and g of node plane c1-1 were written at the end of iteration c1 (tile c1 & 1)
+        fence_async_smem();
+        __syncthreads();
+        const int f = tid - TX;
+        if (f >= 3 && f < 9) {
+            if (c1 >= c0 + 1 && (f < 6 ? STEP != 0 : write_g != 0))
+                tma_store_3d(&maps.out[f], (int)(blockIdx.x * OX) + kGhostX, (int)(blockIdx.y * OY) + 1, c1 - 1,
+                             smem_u32(s_out + ((c1 & 1) * 9 + f) * kOutField));
+            tma_store_commit();
+        }
+        if (f >= 0 && f < 9) tma_store_wait_read<0>();
+    }
     if (SINGLE && own_xy) acc[0] = fma((double)(c1 - c0), kp.st[0].efree, acc[0]);
     // block reduction: warp shuffles, then one warp over the per-warp sums
     __shared__ double red[TY][14];

@@ -58,8 +58,8 @@ k_halo_xy(const __grid_constant__ HaloArgs h, int nx, int ny, int nxp, int64_t p
             l = j % ny;
         }
         const int qx = (k < 0) ? -1 : (k >= nx ? 1 : 0), qy = (l < 0) ? -1 : (l >= ny ? 1 : 0);
-        const int64_t dst = ((int64_t)p * (ny + 2) + l + 1) * nxp + k + 1;
-        const int64_t src = ((int64_t)p * (ny + 2) + (l - qy * ny) + 1) * nxp + (k - qx * nx) + 1;
+        const int64_t dst = ((int64_t)p * (ny + 2) + l + 1) * nxp + k + kGhostX;
+        const int64_t src = ((int64_t)p * (ny + 2) + (l - qy * ny) + 1) * nxp + (k - qx * nx) + kGhostX;
         for (int f = 0; f < h.nfields; f++) {
             const double shift = (f < h.npos) ? qx * sc->rv[f] + qy * sc->rv[3 + f] : 0.0;
             h.f[f][dst] = h.f[f][src] + shift;
@@ -95,7 +95,7 @@ k_halo_xy_u8(uint8_t *f, int nx, int ny, int nxp, int nzl) {
             l = j % ny;
         }
         const int ks = (k < 0) ? nx - 1 : (k >= nx ? 0 : k), ls = (l < 0) ? ny - 1 : (l >= ny ? 0 : l);
-        f[((int64_t)p * (ny + 2) + l + 1) * nxp + k + 1] = f[((int64_t)p * (ny + 2) + ls + 1) * nxp + ks + 1];
+        f[((int64_t)p * (ny + 2) + l + 1) * nxp + k + kGhostX] = f[((int64_t)p * (ny + 2) + ls + 1) * nxp + ks + kGhostX];
     }
 }
 
@@ -127,7 +127,7 @@ k_aos_to_soa(const double *__restrict__ aos, double *s0, double *s1, double *s2,
     const int kk = threadIdx.x;
     for (int mm = threadIdx.y; mm < mt; mm += 8) {
         if (kk < kt) {
-            const int64_t at = ((int64_t)(m0 + mm + 1) * (ny + 2) + l + 1) * nxp + k0 + kk + 1;  // +1: skip the ghosts
+            const int64_t at = ((int64_t)(m0 + mm + 1) * (ny + 2) + l + 1) * nxp + k0 + kk + kGhostX;  // skip the ghosts
 #pragma unroll
             for (int d = 0; d < 3; d++) dst[d][at] = tile[d][kk][mm];
         }
@@ -145,7 +145,7 @@ k_soa_to_aos(const double *__restrict__ s0, const double *__restrict__ s1, const
     const int kk = threadIdx.x;
     for (int mm = threadIdx.y; mm < mt; mm += 8) {
         if (kk < kt) {
-            const int64_t at = ((int64_t)(m0 + mm + 1) * (ny + 2) + l + 1) * nxp + k0 + kk + 1;
+            const int64_t at = ((int64_t)(m0 + mm + 1) * (ny + 2) + l + 1) * nxp + k0 + kk + kGhostX;
 #pragma unroll
             for (int d = 0; d < 3; d++) tile[d][kk][mm] = src[d][at];
         }
@@ -163,7 +163,7 @@ k_mass_to_soa(const double *__restrict__ masses, double *m, double *minv, int nx
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)(i % nx), l = (int)((i / nx) % ny), mm_ = (int)(i / ((int64_t)nx * ny));
         const double v = masses[((int64_t)k * ny + l) * nz + mm_];
-        const int64_t at = ((int64_t)(mm_ + 1) * (ny + 2) + l + 1) * nxp + k + 1;
+        const int64_t at = ((int64_t)(mm_ + 1) * (ny + 2) + l + 1) * nxp + k + kGhostX;
         m[at] = v;
         minv[at] = 1.0 / v;
     }
@@ -174,7 +174,7 @@ k_type_to_soa(const uint8_t *__restrict__ info, uint8_t *type, int nx, int ny, i
     const int64_t n = (int64_t)nx * ny * nz;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)(i % nx), l = (int)((i / nx) % ny), m = (int)(i / ((int64_t)nx * ny));
-        type[((int64_t)(m + 1) * (ny + 2) + l + 1) * nxp + k + 1] = info[((int64_t)k * ny + l) * nz + m] & 15u;
+        type[((int64_t)(m + 1) * (ny + 2) + l + 1) * nxp + k + kGhostX] = info[((int64_t)k * ny + l) * nz + m] & 15u;
     }
 }
 
@@ -264,7 +264,7 @@ static int sg_encode_maps(mm_handle *h) {
     }
     const cuuint64_t dims[3] = {(cuuint64_t)g.nxp, (cuuint64_t)(g.ny + 2), (cuuint64_t)(g.nzl + 3)};
     const cuuint64_t strides[2] = {(cuuint64_t)g.nxp * 8, (cuuint64_t)g.plane * 8};
-    const cuuint32_t box[3] = {(cuuint32_t)TX, (cuuint32_t)g.tile_rows, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)kBoxW, (cuuint32_t)g.tile_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     auto one = [&](CUtensorMap *m, double *p) {
         return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -274,6 +274,13 @@ static int sg_encode_maps(mm_handle *h) {
     for (int c = 0; c < 2; c++)
         for (int d = 0; d < 3; d++) ok = ok && one(&g.tm_x[c][d], g.x[c][d]) && one(&g.tm_v[c][d], g.v[c][d]) && one(&g.tm_g[c][d], g.g[c][d]);
     ok = ok && one(&g.tm_m, g.m) && one(&g.tm_minv, g.minv);
+    const cuuint32_t sbox[3] = {(cuuint32_t)(TX - 2), (cuuint32_t)(g.tile_rows - 2), 1};
+    auto store = [&](CUtensorMap *m, double *p) {
+        return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p, dims, strides, sbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    for (int c = 0; c < 2; c++)
+        for (int d = 0; d < 3; d++) ok = ok && store(&g.ts_x[c][d], g.x[c][d]) && store(&g.ts_v[c][d], g.v[c][d]) && store(&g.ts_g[c][d], g.g[c][d]);
     return ok ? MM_OK : MM_ERR_CUDA;
 }
 
@@ -296,7 +303,7 @@ int sg_setup(mm_handle *h) {
     // The reference enumerates id = (k*ny + l)*nz + m with k along the FIRST domain vector.  Device planes are indexed
     // (x = k fastest, y = l, z = m slowest): the marching direction is the reference's third axis, the lanes run along
     // its first axis.
-    g.nxp = (g.nx + 2 + 1) & ~1;  // one ghost node on each side; even pitch (16-byte rows for the bulk-copy engine)
+    g.nxp = (g.nx + kGhostX + 1 + 1) & ~1;  // ghost nodes on both sides (mm_structured.cuh), even pitch: 16-byte rows for TMA
     g.plane = (int64_t)g.nxp * (g.ny + 2);
     g.npad = g.plane * (g.nzl + 3);  // two halo planes + one spare plane for the prefetch of the marching kernel
     fold_sparams(h->kp, g.sp);
@@ -445,7 +452,6 @@ static void fill_args(mm_handle *h, MarchArgs &a) {
     a.nzl = g.nzl;
     a.nxp = g.nxp;
     a.chunk = g.chunk;
-    a.pf_dist = g.pf_dist;
     for (int d = 0; d < 3; d++) {
         a.x[d] = g.x[g.cx][d];
         a.xo[d] = g.x[g.cx ^ 1][d];
@@ -467,7 +473,7 @@ static int launch_one(mm_handle *h, const MarchArgs &a, int write_g) {
     sg_blocks(h, grid);
     prof_begin(h, STEP);
     // staged variant: kStages planes of the tile in dynamic shared memory (opt-in above 48 KB, once per instantiation)
-    constexpr size_t dyn = (VAR & 2) ? sizeof(double) * kStages * (STEP ? 11 : 3) * TY * TX : 0;
+    constexpr size_t dyn = (VAR & 2) ? sizeof(double) * (kStages * (STEP ? 11 : 3) * TY * kBoxW + 2 * 9 * kOutField) : 0;
     if (dyn > 0) {
         static bool configured[64] = {false};
         if (!configured[h->device & 63]) {
@@ -485,6 +491,13 @@ static int launch_one(mm_handle *h, const MarchArgs &a, int write_g) {
         }
         maps.in[9] = g.tm_m;
         maps.in[10] = g.tm_minv;
+        // what the launch writes: the other x / v sets; the gradient goes where a.go points (FORCE: current set, STEP: other)
+        const int gx = g.cx ^ 1, gv = g.cv ^ 1, gg = (a.go[0] == g.g[g.cg][0]) ? g.cg : (g.cg ^ 1);
+        for (int d = 0; d < 3; d++) {
+            maps.out[d] = g.ts_x[gx][d];
+            maps.out[3 + d] = g.ts_v[gv][d];
+            maps.out[6 + d] = g.ts_g[gg][d];
+        }
     } else {
         memset(&maps, 0, sizeof(maps));
     }
@@ -519,15 +532,15 @@ static int launch_march(mm_handle *h, const MarchArgs &a, bool step, int rot, in
     int var = h->sg.variant & 15;
     if (!stageable) var &= ~2;
     if (var & 2) var &= ~1;  // the refill of a stage relies on the block barrier
+    if (!(var & 2)) var &= ~8;
     switch (var) {  // tuning variants kept for the measurements in profiles/ (bits: see k_march)
         case 1: return launch_sel<true, 1>(h, a, step, rot, vm, lean, write_g);
         case 2: return launch_sel<true, 2>(h, a, step, rot, vm, lean, write_g);
         case 4: return launch_sel<true, 4>(h, a, step, rot, vm, lean, write_g);
         case 5: return launch_sel<true, 5>(h, a, step, rot, vm, lean, write_g);
         case 6: return launch_sel<true, 6>(h, a, step, rot, vm, lean, write_g);
-        case 8: return launch_sel<true, 8>(h, a, step, rot, vm, lean, write_g);
-        case 9: return launch_sel<true, 9>(h, a, step, rot, vm, lean, write_g);
-        case 12: return launch_sel<true, 12>(h, a, step, rot, vm, lean, write_g);
+        case 10: return launch_sel<true, 10>(h, a, step, rot, vm, lean, write_g);
+        case 14: return launch_sel<true, 14>(h, a, step, rot, vm, lean, write_g);
         default: return launch_sel<true, 0>(h, a, step, rot, vm, lean, write_g);
     }
 }

@@ -8,6 +8,9 @@
 
 namespace mm {
 
+constexpr int kGhostX = 2;  // padded column of node k = 0
+constexpr int kBoxW = 34;   // width of the TMA load box of a 32-lane tile (starts one node before the tile: even column)
+
 // Per-state constants of the marching kernel (mm_march.cuh: metric formulation), folded on the host in fold_sparams:
 //   Hs = 4 H is what the separable stencil produces;  d = Hs Hs^T - c0;  Sq = Bq d;  E = 1/4 d:Sq;  D' = D / 4 = Sq Hs
 struct SState {
@@ -38,8 +41,11 @@ struct StepConsts {
 
 // SoA planes in z-major order, padded by one ghost node on each side of every axis (periodic images, kept current by
 // sg_halo; positions of ghosts already carry the domain-vector shift):
-//   index(k, l, p) = (p * (ny + 2) + l + 1) * nxp + k + 1,   k = -1 .. nx, l = -1 .. ny, p = 0 (lower halo), 1..nzl (owned),
-//   nzl + 1 (upper halo); nxp = nx + 2 rounded up to an even pitch.  A z-slab of a multi-GPU decomposition is one contiguous
+//   index(k, l, p) = (p * (ny + 2) + l + 1) * nxp + k + kGhostX,   k = -1 .. nx, l = -1 .. ny, p = 0 (lower halo), 1..nzl
+//   (owned), nzl + 1 (upper halo); nxp = nx + kGhostX + 1 rounded up to an even pitch.  kGhostX = 2 (one unused column before
+//   the x ghost): TMA boxes of 8-byte elements must start on 16 bytes, i.e. on an EVEN column (measured:
+//   profiles/microbench/tma_store_probe.cu), and with two columns in front both the load box of a tile (node k0 - 2, 34
+//   wide) and its store box (first owned node k0, 30 wide) do.  A z-slab of a multi-GPU decomposition is one contiguous
 // range of planes and its halos are whole (padded) planes; a tile of the marching kernel never wraps.
 struct SGrid {
     int active = 0;
@@ -53,6 +59,7 @@ struct SGrid {
     uint8_t *type = nullptr;
     int cx = 0, cv = 0, cg = 0;     // which copy is current
     CUtensorMap tm_x[2][3], tm_v[2][3], tm_g[2][3], tm_m, tm_minv;  // load descriptors of the arrays above
+    CUtensorMap ts_x[2][3], ts_v[2][3], ts_g[2][3];                  // store descriptors
     int tma_ok = 0;                 // descriptors encoded (driver entry point available, pitch constraints met)
     StepConsts *d_sc = nullptr;
     SParams *d_sp = nullptr;        // device copy of sp
@@ -60,22 +67,21 @@ struct SGrid {
     double *d_partials = nullptr;   // [nblocks][kRedSlots]
     int nblocks = 0, nblocks_alloc = 0;
     int tile_rows = 8;              // TY of the marching kernel (warps per block)
-    int variant = 0;                // tuning bits of the marching kernel (k_march VAR)
-    int pf_dist = 3;                // L2 prefetch distance in planes
+    int variant = 2;                // tuning bits of the marching kernel (k_march VAR); default: TMA loads
     int chunk = 32;                 // owned planes per block along z
     SParams sp;
 };
 
-// Tensor maps (TMA descriptors) of the arrays one launch of the staged kernel variant reads: box = TX x TY x 1 nodes of a
-// padded plane; coordinates outside the array read as zero (the partial tiles at the upper x / y edge)
+// Tensor maps (TMA descriptors) of the arrays one launch of the staged kernel variant reads: box = kBoxW x TY x 1 nodes of
+// a padded plane; coordinates outside the array read as zero (the partial tiles at the upper x / y edge)
 struct alignas(64) TmaMaps {
     CUtensorMap in[11];  // x0 x1 x2 v0 v1 v2 g0 g1 g2 m 1/m
+    CUtensorMap out[9];  // x0 x1 x2 v0 v1 v2 g0 g1 g2 of the sets the launch writes; box = the (TX-2) x (TY-2) owned nodes
 };
 
 struct MarchArgs {
     int nx, ny, nzl, chunk;
     int nxp;      // row pitch of the padded planes
-    int pf_dist;  // L2 prefetch distance in planes (k_march VAR & 8)
     const double *x[3];
     double *xo[3];
     const double *v[3];

@@ -43,7 +43,11 @@ if __name__ == "__main__":
     grid = os.environ.get("GRID", "256")
     for a in sys.argv[3].split():
         env = dict(os.environ, MICMEC_B200_LIB=os.path.join(ROOT, "profiles", "ablate", "lib_%s.so" % a))
-        out = subprocess.run([sys.executable, "-c", CHILD, ens, variant, grid], env=env, capture_output=True, text=True)
+        try:  # an ablated build may hang (e.g. no barriers + staged loads): bound every child
+            out = subprocess.run([sys.executable, "-c", CHILD, ens, variant, grid], env=env, capture_output=True, text=True, timeout=90)
+        except subprocess.TimeoutExpired:
+            print(json.dumps({"ablate": int(a), "ensemble": ens, "variant": int(variant), "ms_per_step": None, "err": "timeout"}), flush=True)
+            continue
         ms = [l for l in out.stdout.splitlines() if l.startswith("MS_PER_STEP")]
         print(json.dumps({"ablate": int(a), "ensemble": ens, "variant": int(variant), "ms_per_step": float(ms[0].split()[1]) if ms else None,
                           "err": None if ms else out.stderr[-300:]}), flush=True)
