@@ -138,6 +138,7 @@ int mm_destroy(mm_handle *h) {
     cudaFree(h->d_rvecs);
     cudaFree(h->d_red);
     cudaFree(h->d_halo);
+    comm_peer_free(h);
     cudaFree(h->d_rvecs_batch);
     cudaFree(h->d_vcell);
     cudaFree(h->d_rep);

@@ -80,6 +80,14 @@ struct mm_handle {
     double *d_vcell = nullptr;        // [6][ncells]
     double *d_rep = nullptr;          // [nreplicas][8]: energy, virial(6), pad
     double *d_halo = nullptr; // packed halo messages: send up / send down / recv from down / recv from up, 9 planes each
+    // peer mode (mm_comm.cu): halo planes and the 16-double sums are stored directly into the neighbours' memory over
+    // NVLink (CUDA IPC mappings of one block per rank) and handed over with system-scope flags; NCCL only bootstraps
+    int peer_mode = 0;
+    char *d_peer = nullptr;         // this rank's peer-visible block: flags, mailboxes, inboxes
+    char *peer_base[16] = {nullptr};  // mapped base of every rank's block (own entry = d_peer)
+    char **d_peer_base = nullptr;   // device copy of peer_base
+    void *d_peer_ctl = nullptr;     // local epoch counters (PeerCtl)
+    int64_t peer_plane = 0;         // padded plane (nodes) the inboxes were sized for
     mm::SGrid sg;
 };
 
@@ -119,5 +127,6 @@ int sg_set_chunk(mm_handle *h, int chunk);
 int comm_halo(mm_handle *h, double **fields, int nfields, int npos);
 int comm_allreduce(mm_handle *h, double *buf, int count);
 int comm_reduce_partials(mm_handle *h, const double *pc, int nbc, const double *pn, int nbn, const double *pd, int nbd);
+void comm_peer_free(mm_handle *h);
 
 }  // namespace mm
