@@ -136,6 +136,8 @@ k_unpack(const __grid_constant__ PackArgs a, int64_t plane, int nzl, const doubl
 struct PeerCtl {
     unsigned long long halo_epoch, red_epoch;
     unsigned int halo_done, pad;
+    unsigned long long fused_epoch;  // fused halo exchanges completed (k_halo_xy_fused)
+    unsigned int fused_done, pad2;
 };
 
 constexpr size_t kPeerFlagBytes = 1024;
@@ -247,6 +249,11 @@ k_peer_allreduce(const double *pc, int nbc, const double *pn, int nbn, const dou
 }
 
 void comm_peer_free(mm_handle *h) {
+    for (int s = 0; s < 2; s++) {
+        if (h->peer_soa[s] && (s == 0 || h->peer_soa[1] != h->peer_soa[0])) cudaIpcCloseMemHandle(h->peer_soa[s]);
+    }
+    h->peer_soa[0] = h->peer_soa[1] = nullptr;
+    if (h->slab_count > 1) h->sg.fused = 0;
     for (int r = 0; r < 16; r++)
         if (h->peer_base[r] && h->peer_base[r] != h->d_peer) cudaIpcCloseMemHandle(h->peer_base[r]);
     for (int r = 0; r < 16; r++) h->peer_base[r] = nullptr;
@@ -257,6 +264,83 @@ void comm_peer_free(mm_handle *h) {
     h->d_peer_base = nullptr;
     h->d_peer_ctl = nullptr;
     h->peer_mode = 0;
+}
+
+// Fused halo (mm_structured.cuh: MarchArgs): map the node-array blocks of the two z neighbours, so that the marching
+// kernel can store its boundary planes straight into their halo planes.  Collective; all ranks agree on the outcome.
+struct SoaInfo {
+    cudaIpcMemHandle_t hdl;
+    int64_t stride;
+    int32_t nzl, pad;
+};
+
+static int peer_setup_fused(mm_handle *h) {
+    const int P = h->slab_count, r = h->slab_rank;
+    const int up = (r + 1) % P, down = (r + P - 1) % P;
+    ncclComm_t comm = (ncclComm_t)h->comm;
+    SGrid &g = h->sg;
+    const char *env = getenv("MICMEC_B200_FUSED");
+    int ok = (env && atoi(env) == 0) ? 0 : 1;
+    SoaInfo mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaIpcGetMemHandle(&mine.hdl, g.block) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    mine.stride = g.stride;
+    mine.nzl = g.nzl;
+    unsigned char *d_info = nullptr;
+    int *d_ok = nullptr;
+    MM_CUDA(cudaMalloc(&d_info, sizeof(SoaInfo) * (size_t)P));
+    MM_CUDA(cudaMalloc(&d_ok, sizeof(int)));
+    MM_CUDA(cudaMemcpyAsync(d_info + sizeof(SoaInfo) * (size_t)r, &mine, sizeof(SoaInfo), cudaMemcpyHostToDevice, h->stream));
+    MM_NCCL(g_nccl.AllGather(d_info + sizeof(SoaInfo) * (size_t)r, d_info, sizeof(SoaInfo), ncclUint8, comm, h->stream));
+    std::vector<SoaInfo> all(P);
+    MM_CUDA(cudaMemcpyAsync(all.data(), d_info, sizeof(SoaInfo) * (size_t)P, cudaMemcpyDeviceToHost, h->stream));
+    MM_CUDA(cudaStreamSynchronize(h->stream));
+    if (ok) {
+        void *pd = nullptr, *pu = nullptr;
+        if (cudaIpcOpenMemHandle(&pd, all[down].hdl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+        } else if (up == down) {
+            pu = pd;
+        } else if (cudaIpcOpenMemHandle(&pu, all[up].hdl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            cudaIpcCloseMemHandle(pd);
+            pd = nullptr;
+            ok = 0;
+        }
+        h->peer_soa[0] = pd;
+        h->peer_soa[1] = pu;
+    }
+    MM_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    MM_NCCL(g_nccl.AllReduce(d_ok, d_ok, 1, 2 /* ncclInt32 */, ncclMin, comm, h->stream));
+    int all_ok = 0;
+    MM_CUDA(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    MM_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d_info);
+    cudaFree(d_ok);
+    if (!all_ok) {
+        for (int s = 0; s < 2; s++)
+            if (h->peer_soa[s] && (s == 0 || h->peer_soa[1] != h->peer_soa[0])) cudaIpcCloseMemHandle(h->peer_soa[s]);
+        h->peer_soa[0] = h->peer_soa[1] = nullptr;
+        return MM_OK;  // peer mode 1 (inbox copies) stays on
+    }
+    const int nb[2] = {down, up};
+    for (int s = 0; s < 2; s++) {
+        g.nb_block[s] = (double *)h->peer_soa[s];
+        g.nb_stride[s] = all[nb[s]].stride;
+        g.nb_nzl[s] = all[nb[s]].nzl;
+    }
+    // my lower boundary plane lands in the upper halo of the rank below: its "from above" counter; and vice versa
+    g.nb_flag[0] = reinterpret_cast<unsigned long long *>(h->peer_base[down]) + 33;
+    g.nb_flag[1] = reinterpret_cast<unsigned long long *>(h->peer_base[up]) + 32;
+    g.halo_flags = reinterpret_cast<unsigned long long *>(h->d_peer) + 32;  // [0] from below, [1] from above
+    g.halo_epoch = &reinterpret_cast<PeerCtl *>(h->d_peer_ctl)->fused_epoch;
+    g.halo_done = &reinterpret_cast<PeerCtl *>(h->d_peer_ctl)->fused_done;
+    g.fused = 1;
+    return MM_OK;
 }
 
 // Collective over the slab communicator: allocate and exchange the peer blocks.  Every rank ends with the same
@@ -322,7 +406,7 @@ static int peer_setup(mm_handle *h) {
     MM_CUDA(cudaStreamSynchronize(h->stream));
     h->peer_plane = plane;
     h->peer_mode = 1;
-    return MM_OK;
+    return peer_setup_fused(h);
 }
 
 int comm_halo(mm_handle *h, double **fields, int nfields, int npos) {

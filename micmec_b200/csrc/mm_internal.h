@@ -88,6 +88,7 @@ struct mm_handle {
     char **d_peer_base = nullptr;   // device copy of peer_base
     void *d_peer_ctl = nullptr;     // local epoch counters (PeerCtl)
     int64_t peer_plane = 0;         // padded plane (nodes) the inboxes were sized for
+    void *peer_soa[2] = {nullptr, nullptr};  // IPC mappings of the neighbours' node-array blocks (fused halo, sg.nb_block)
     mm::SGrid sg;
 };
 

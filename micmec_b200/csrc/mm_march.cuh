@@ -99,6 +99,17 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // generic-proxy writes to shared memory -> visible to the async proxy (executed by the writers before the barrier)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Delivery of one boundary-plane triple into a neighbour's halo plane (fused halo exchange).  Deliberately NOT inlined:
+// it runs for 2 of the planes of a slab, and as inlined predicated stores it costs every plane 18 address computations
+// and 18 predicated-off STG (measured: +10 % on the whole step).
+__device__ __noinline__ void deliver3(double *d0, double *d1, double *d2, unsigned at, bool pred, double v0, double v1, double v2) {
+    if (pred) {
+        d0[at] = v0;
+        d1[at] = v1;
+        d2[at] = v2;
+    }
+}
+
 // all states of a cell, Boltzmann-mixed (mmff.py:377-398); the mixing is linear in the gradient, hence in Sq.
 template <bool SINGLE, bool WANT_VIR>
 __device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp, int type, double &e, double D[9],
@@ -223,6 +234,12 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         for (int i = 0; i < 9; i++) M[i] = sc.Mvel[i];
     }
     const double dt = sc.dt, hdt = 0.5 * sc.dt;
+    // third domain vector in the frame of the positions this launch WRITES (rotated with them when ROT): the shift of the
+    // boundary planes delivered across the periodic end of the slab ring
+    double cw[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+        cw[j] = ROT ? fma(sc.rv[8], R[6 + j], fma(sc.rv[7], R[3 + j], sc.rv[6] * R[j])) : sc.rv[6 + j];
     const int rowp = (row + 1 < TY) ? row + 1 : row;
     const int rowm = (row > 0) ? row - 1 : row;
 
@@ -292,8 +309,9 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     // One plane.  CELL: cell layer p-1 (planes p-1 and p) exists; NODE: node plane p-1 (cell layers p-2, p-1) is
     // completed.  The first two planes of a chunk are peeled (CELL / NODE false), so that the steady-state loop has no
     // uniform branches and its constant loads stay on the uniform datapath.
-    auto plane_body = [&](auto cell_tag, auto node_tag, const int p) {
+    auto plane_body = [&](auto cell_tag, auto node_tag, auto halo_tag, const int p) {
         constexpr bool CELL = decltype(cell_tag)::value, NODE = decltype(node_tag)::value;
+        constexpr bool HALO = decltype(halo_tag)::value;  // this plane may be a boundary plane of the slab (fused halo)
         double cx0, cx1, cx2, cv[3] = {0, 0, 0}, cg[3] = {0, 0, 0}, cm = 0.0, cminv = 0.0;
         const unsigned st = it % kStages;
         if (TMA) {
@@ -363,6 +381,12 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
                 const bool px = own_xy && p < c1;
 #pragma unroll
                 for (int j = 0; j < 3; j++) st_if(px, a.xo[j] + idx, r[j]);
+                if (HALO && a.fused && p == 1)
+                    deliver3(a.halo_lo[0], a.halo_lo[1], a.halo_lo[2], idx, px, fma(a.wrap_lo, cw[0], r[0]),
+                             fma(a.wrap_lo, cw[1], r[1]), fma(a.wrap_lo, cw[2], r[2]));
+                if (HALO && a.fused && p == a.nzl)
+                    deliver3(a.halo_hi[0], a.halo_hi[1], a.halo_hi[2], idx, px, fma(a.wrap_hi, cw[0], r[0]),
+                             fma(a.wrap_hi, cw[1], r[1]), fma(a.wrap_hi, cw[2], r[2]));
             }
         }
         if (TST) fence_async_smem();  // the tile parts written since the last barrier (x of plane p; v, g of plane p-2)
@@ -481,6 +505,8 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
                         st_if(own_xy, a.vo[j] + at, vn[j]);
                     }
                 }
+                if (HALO && !TST && a.fused && p == 2) deliver3(a.halo_lo[3], a.halo_lo[4], a.halo_lo[5], at, own_xy, vn[0], vn[1], vn[2]);
+                if (HALO && !TST && a.fused && p == a.nzl + 1) deliver3(a.halo_hi[3], a.halo_hi[4], a.halo_hi[5], at, own_xy, vn[0], vn[1], vn[2]);
                 const double mo = own_xy ? mprev : 0.0;
                 const double mx = mo * vn[0], my = mo * vn[1], mz = mo * vn[2];
                 acc[7] = fma(mx, vn[0], acc[7]);
@@ -501,6 +527,8 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
                 const bool pg = own_xy && write_g;
 #pragma unroll
                 for (int j = 0; j < 3; j++) st_if(pg, a.go[j] + at, g[j]);
+                if (HALO && a.fused && p == 2) deliver3(a.halo_lo[6], a.halo_lo[7], a.halo_lo[8], at, pg, g[0], g[1], g[2]);
+                if (HALO && a.fused && p == a.nzl + 1) deliver3(a.halo_hi[6], a.halo_hi[7], a.halo_hi[8], at, pg, g[0], g[1], g[2]);
             }
             if (!LEAN) acc[13] += own_xy ? fma(g[0], g[0], fma(g[1], g[1], g[2] * g[2])) : 0.0;
         }
@@ -518,11 +546,17 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         it++;
     };
 
-    plane_body(std::false_type{}, std::false_type{}, c0 - 1);
-    plane_body(std::true_type{}, std::false_type{}, c0);
-    // two planes per trip: the plane-to-plane hand-over of the carried values becomes register renaming instead of ~34 MOVs
+    // The boundary planes of a slab (1, nzl: positions; one iteration later: velocities, gradients) can only come up in the
+    // first three and the last two iterations of a chunk: only those bodies carry the delivery code of the fused halo.
+    constexpr std::true_type T{};
+    constexpr std::false_type F{};
+    plane_body(F, F, T, c0 - 1);
+    plane_body(T, F, T, c0);
+    plane_body(T, T, T, c0 + 1);
 #pragma unroll UNR
-    for (int p = c0 + 1; p <= c1; p++) plane_body(std::true_type{}, std::true_type{}, p);
+    for (int p = c0 + 2; p <= c1 - 2; p++) plane_body(T, T, F, p);
+#pragma unroll 1
+    for (int p = max(c0 + 2, c1 - 1); p <= c1; p++) plane_body(T, T, T, p);
 
     if (TST) {  // drain: v and g of node plane c1-1 were written at the end of iteration c1 (tile c1 & 1)
         fence_async_smem();

@@ -42,6 +42,12 @@ struct HaloArgs {
     int npos;  // the first npos fields are position components 0, 1, 2
 };
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(256)
 k_halo_xy(const __grid_constant__ HaloArgs h, int nx, int ny, int nxp, int64_t plane, int nzl, const StepConsts *sc) {
     const int per_plane = 2 * (nx + 2) + 2 * ny;  // two full ghost rows (with corners) + two ghost columns
@@ -63,6 +69,66 @@ k_halo_xy(const __grid_constant__ HaloArgs h, int nx, int ny, int nxp, int64_t p
         for (int f = 0; f < h.nfields; f++) {
             const double shift = (f < h.npos) ? qx * sc->rv[f] + qy * sc->rv[3 + f] : 0.0;
             h.f[f][dst] = h.f[f][src] + shift;
+        }
+    }
+}
+
+// Fused-halo variant (the marching kernel has already stored the boundary planes into the neighbours' halo planes).
+// Slabs: block 0 first announces the delivery - the marching kernel has completed (stream order), a system-scope fence
+// makes its peer stores visible before the two counters move - then every block fills the x / y ghosts of the owned planes,
+// waits until both neighbours have announced this exchange too (epoch = exchanges completed, advanced by the last block),
+// and fills the ghosts of the two halo planes.  Their nodes were written by another GPU: read them past the L1.
+__global__ void __launch_bounds__(256)
+k_halo_xy_fused(const __grid_constant__ HaloArgs h, int nx, int ny, int nxp, int nzl, const StepConsts *sc,
+                const unsigned long long *flags, unsigned long long *epoch, unsigned int *done_blocks, unsigned long long *flag_lo,
+                unsigned long long *flag_hi) {
+    const int per_plane = 2 * (nx + 2) + 2 * ny;
+    auto ghost = [&](int64_t i, int p, bool remote) {
+        int j = (int)(i % per_plane), k, l;
+        if (j < 2 * (nx + 2)) {
+            l = (j < nx + 2) ? -1 : ny;
+            k = (j % (nx + 2)) - 1;
+        } else {
+            j -= 2 * (nx + 2);
+            k = (j < ny) ? -1 : nx;
+            l = j % ny;
+        }
+        const int qx = (k < 0) ? -1 : (k >= nx ? 1 : 0), qy = (l < 0) ? -1 : (l >= ny ? 1 : 0);
+        const int64_t dst = ((int64_t)p * (ny + 2) + l + 1) * nxp + k + kGhostX;
+        const int64_t src = ((int64_t)p * (ny + 2) + (l - qy * ny) + 1) * nxp + (k - qx * nx) + kGhostX;
+        for (int f = 0; f < h.nfields; f++) {
+            const double shift = (f < h.npos) ? qx * sc->rv[f] + qy * sc->rv[3 + f] : 0.0;
+            h.f[f][dst] = (remote ? __ldcg(h.f[f] + src) : h.f[f][src]) + shift;
+        }
+    };
+    // exchanges completed so far: read by every block before the last one to finish can advance it
+    const unsigned long long want = flags ? ld_acquire_sys_u64(epoch) + 1 : 0ull;
+    if (flags && blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        atomicAdd_system(flag_lo, 1ull);
+        atomicAdd_system(flag_hi, 1ull);
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = first; i < (int64_t)per_plane * nzl; i += stride) ghost(i, 1 + (int)(i / per_plane), false);
+    if (flags) {
+        if (threadIdx.x == 0) {
+            while (ld_acquire_sys_u64(flags) < want) {
+            }
+            while (ld_acquire_sys_u64(flags + 1) < want) {
+            }
+        }
+        __syncthreads();
+    }
+    for (int64_t i = first; i < 2 * (int64_t)per_plane; i += stride) ghost(i, (i / per_plane) ? nzl + 1 : 0, flags != nullptr);
+    if (flags) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(done_blocks, 1u) == gridDim.x - 1) {
+                *done_blocks = 0;
+                *epoch = want;
+                __threadfence();
+            }
         }
     }
 }
@@ -284,6 +350,9 @@ static int sg_encode_maps(mm_handle *h) {
     return ok ? MM_OK : MM_ERR_CUDA;
 }
 
+// index of an array inside the block: quantity 0 x / 1 v / 2 g, copy c, component d; 18 = m, 19 = 1/m
+static inline int sg_array(int quantity, int c, int d) { return (quantity * 2 + c) * 3 + d; }
+
 bool sg_eligible(const mm_handle *h) {
     return h->structured && h->model == MM_MODEL_ORIGINAL && h->nx >= 2 && h->ny >= 2 && h->nz >= 2;
 }
@@ -307,20 +376,29 @@ int sg_setup(mm_handle *h) {
     g.plane = (int64_t)g.nxp * (g.ny + 2);
     g.npad = g.plane * (g.nzl + 3);  // two halo planes + one spare plane for the prefetch of the marching kernel
     fold_sparams(h->kp, g.sp);
-    const size_t bytes = sizeof(double) * g.npad;
+    // all node arrays in one allocation: array a at block + a * stride (order: sg_array)
+    // (the stride is skewed by an odd number of 256-byte lines: with a power-of-two-ish stride the same node of all 20
+    // arrays falls on the same memory channel and the 20 streams of the marching kernel queue up there)
+    g.stride = ((g.npad + 31) & ~(int64_t)31) + 32 * 37;
+    const size_t bytes = sizeof(double) * (size_t)g.stride * 20;
+    MM_CUDA(cudaMalloc(&g.block, bytes));
+    MM_CUDA(cudaMemsetAsync(g.block, 0, bytes, h->stream));
     for (int c = 0; c < 2; c++)
         for (int d = 0; d < 3; d++) {
-            MM_CUDA(cudaMalloc(&g.x[c][d], bytes));
-            MM_CUDA(cudaMalloc(&g.v[c][d], bytes));
-            MM_CUDA(cudaMalloc(&g.g[c][d], bytes));
-            MM_CUDA(cudaMemsetAsync(g.x[c][d], 0, bytes, h->stream));
-            MM_CUDA(cudaMemsetAsync(g.v[c][d], 0, bytes, h->stream));
-            MM_CUDA(cudaMemsetAsync(g.g[c][d], 0, bytes, h->stream));
+            g.x[c][d] = g.block + (size_t)g.stride * sg_array(0, c, d);
+            g.v[c][d] = g.block + (size_t)g.stride * sg_array(1, c, d);
+            g.g[c][d] = g.block + (size_t)g.stride * sg_array(2, c, d);
         }
-    MM_CUDA(cudaMalloc(&g.m, bytes));
-    MM_CUDA(cudaMalloc(&g.minv, bytes));
-    MM_CUDA(cudaMemsetAsync(g.m, 0, bytes, h->stream));
-    MM_CUDA(cudaMemsetAsync(g.minv, 0, bytes, h->stream));
+    g.m = g.block + (size_t)g.stride * 18;
+    g.minv = g.block + (size_t)g.stride * 19;
+    // single slab: the "neighbours" are the periodic images of the slab itself
+    for (int s = 0; s < 2; s++) {
+        g.nb_block[s] = g.block;
+        g.nb_stride[s] = g.stride;
+        g.nb_nzl[s] = g.nzl;
+        g.nb_flag[s] = nullptr;
+    }
+    g.fused = (h->slab_count <= 1) ? 1 : 0;  // slabs switch it on once the peers are mapped (mm_comm.cu)
     MM_CUDA(cudaMalloc(&g.type, g.npad));
     g.tma_ok = sg_encode_maps(h) == MM_OK ? 1 : 0;
     MM_CUDA(cudaMalloc(&g.d_sc, sizeof(StepConsts)));
@@ -347,14 +425,8 @@ int sg_setup(mm_handle *h) {
 
 void sg_free(mm_handle *h) {
     SGrid &g = h->sg;
-    for (int c = 0; c < 2; c++)
-        for (int d = 0; d < 3; d++) {
-            cudaFree(g.x[c][d]);
-            cudaFree(g.v[c][d]);
-            cudaFree(g.g[c][d]);
-        }
-    cudaFree(g.m);
-    cudaFree(g.minv);
+    cudaFree(g.block);
+    g.block = nullptr;
     cudaFree(g.type);
     cudaFree(g.d_sc);
     cudaFree(g.d_sp);
@@ -391,6 +463,15 @@ int sg_halo(mm_handle *h, bool pos, bool vel, bool grad) {
     if (grad)
         for (int d = 0; d < 3; d++) ha.f[ha.nfields++] = g.g[g.cg][d];
     if (ha.nfields == 0) return MM_OK;
+    const int mask = (pos ? 1 : 0) | (vel ? 2 : 0) | (grad ? 4 : 0);
+    if (g.fused && g.fused_mask == mask) {  // the marching kernel delivered the boundary planes itself
+        g.fused_mask = 0;
+        k_halo_xy_fused<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * (g.nzl + 2), 256), 256, 0, h->stream>>>(
+            ha, g.nx, g.ny, g.nxp, g.nzl, g.d_sc, g.halo_flags, g.halo_epoch, g.halo_done, g.nb_flag[0], g.nb_flag[1]);
+        h->launches++;
+        return MM_OK;
+    }
+    g.fused_mask = 0;
     k_halo_xy<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * g.nzl, 256), 256, 0, h->stream>>>(ha, g.nx, g.ny, g.nxp, g.plane, g.nzl, g.d_sc);
     h->launches++;
     if (h->slab_count > 1) return comm_halo(h, ha.f, ha.nfields, ha.npos);  // (padded) planes travel between the slabs
@@ -465,6 +546,26 @@ static void fill_args(mm_handle *h, MarchArgs &a) {
     a.type = g.type;
     a.sc = g.d_sc;
     a.partials = g.d_partials;
+    a.fused = 0;
+    a.wrap_lo = a.wrap_hi = 0.0;
+    for (int f = 0; f < 9; f++) a.halo_lo[f] = a.halo_hi[f] = nullptr;
+}
+
+// Fused halo: targets of the boundary planes of what a launch writes (array indices ax / av / ag inside the block)
+static void fill_fused(mm_handle *h, MarchArgs &a, int cx_out, int cv_out, int cg_out) {
+    SGrid &g = h->sg;
+    if (!g.fused) return;
+    a.fused = 1;
+    const int P = h->slab_count, r = h->slab_rank;
+    for (int f = 0; f < 9; f++) {
+        const int arr = f < 3 ? sg_array(0, cx_out, f) : f < 6 ? sg_array(1, cv_out, f - 3) : sg_array(2, cg_out, f - 6);
+        // own plane 1 -> plane nzl' + 1 of the slab below; own plane nzl -> plane 0 of the slab above (pointers biased by
+        // the own plane index, so that the kernel adds the same element index as for its own store)
+        a.halo_lo[f] = g.nb_block[0] + (size_t)g.nb_stride[0] * arr + (int64_t)(g.nb_nzl[0] + 1 - 1) * g.plane;
+        a.halo_hi[f] = g.nb_block[1] + (size_t)g.nb_stride[1] * arr - (int64_t)g.nzl * g.plane;
+    }
+    a.wrap_lo = (r == 0) ? 1.0 : 0.0;       // below rank 0 sits the last slab: its upper halo is my plane 1 PLUS c
+    a.wrap_hi = (r == P - 1) ? -1.0 : 0.0;  // above the last rank sits slab 0: its lower halo is my plane nzl MINUS c
 }
 
 template <int STEP, bool SINGLE, int ROT, int VM, bool LEAN, int VAR, int TY>
@@ -532,7 +633,7 @@ static int launch_march(mm_handle *h, const MarchArgs &a, bool step, int rot, in
     int var = h->sg.variant & 15;
     if (!stageable) var &= ~2;
     if (var & 2) var &= ~1;  // the refill of a stage relies on the block barrier
-    if (!(var & 2)) var &= ~8;
+    if (!(var & 2) || h->sg.fused) var &= ~8;
     switch (var) {  // tuning variants kept for the measurements in profiles/ (bits: see k_march)
         case 1: return launch_sel<true, 1>(h, a, step, rot, vm, lean, write_g);
         case 2: return launch_sel<true, 2>(h, a, step, rot, vm, lean, write_g);
@@ -553,7 +654,9 @@ int sg_force(mm_handle *h, bool write_g, int rot) {
     MarchArgs a;
     fill_args(h, a);
     for (int d = 0; d < 3; d++) a.go[d] = g.g[g.cg][d];
+    fill_fused(h, a, g.cx ^ 1, g.cv ^ 1, g.cg);
     const int rc = launch_march(h, a, false, rot, 0, false, write_g ? 1 : 0);
+    g.fused_mask = g.fused ? ((rot == 2 ? 1 : 0) | (write_g ? 4 : 0)) : 0;
     if (rot == 2) g.cx ^= 1;
     return rc;
 }
@@ -565,7 +668,9 @@ int sg_step(mm_handle *h, bool write_g, int vm, bool lean) {
     SGrid &g = h->sg;
     MarchArgs a;
     fill_args(h, a);
+    fill_fused(h, a, g.cx ^ 1, g.cv ^ 1, g.cg ^ 1);
     const int rc = launch_march(h, a, true, 0, vm, lean && vm != 2, write_g ? 1 : 0);
+    g.fused_mask = g.fused ? (3 | (write_g ? 4 : 0)) : 0;
     g.cx ^= 1;
     g.cv ^= 1;
     if (write_g) g.cg ^= 1;

@@ -52,6 +52,8 @@ struct SGrid {
     int nx = 0, ny = 0, nzl = 0;
     int nxp = 0;                    // row pitch in nodes
     int64_t plane = 0, npad = 0;    // padded plane (nxp * (ny + 2)) and array size in nodes
+    double *block = nullptr;        // ONE allocation behind the 20 arrays below (array a at block + a * stride): the peers
+    int64_t stride = 0;             // of a z-slab map it with a single CUDA IPC handle (array order: see sg_array)
     double *x[2][3] = {{nullptr}};  // ping-pong: kernels that move nodes read one set and write the other
     double *v[2][3] = {{nullptr}};
     double *g[2][3] = {{nullptr}};
@@ -61,6 +63,17 @@ struct SGrid {
     CUtensorMap tm_x[2][3], tm_v[2][3], tm_g[2][3], tm_m, tm_minv;  // load descriptors of the arrays above
     CUtensorMap ts_x[2][3], ts_v[2][3], ts_g[2][3];                  // store descriptors
     int tma_ok = 0;                 // descriptors encoded (driver entry point available, pitch constraints met)
+    // fused halo (see MarchArgs): where the z neighbours' copies of this slab's arrays live (own block when there is one
+    // slab), their plane counts, and what the last marching launch already delivered
+    double *nb_block[2] = {nullptr, nullptr};  // [0] below (rank - 1), [1] above (rank + 1)
+    int64_t nb_stride[2] = {0, 0};
+    int nb_nzl[2] = {0, 0};
+    unsigned long long *nb_flag[2] = {nullptr, nullptr};  // the neighbours' arrival counters for planes coming from this rank
+    unsigned long long *halo_flags = nullptr;  // own arrival counters [from below, from above] (slabs; null for one slab)
+    unsigned long long *halo_epoch = nullptr;  // fused exchanges completed (device counter, advanced by k_halo_xy_fused)
+    unsigned int *halo_done = nullptr;         // its block counter
+    int fused = 0;                  // k_march also writes the boundary planes into the neighbours' halo planes
+    int fused_mask = 0;             // fields delivered by the last launch: 1 positions, 2 velocities, 4 gradients
     StepConsts *d_sc = nullptr;
     SParams *d_sp = nullptr;        // device copy of sp
     StepConsts *h_sc = nullptr;     // pinned staging
@@ -90,6 +103,15 @@ struct MarchArgs {
     double *go[3];
     const double *m, *minv;
     const uint8_t *type;
+    // Fused halo exchange: the two boundary planes of everything a launch writes are ALSO stored into the halo planes
+    // of the z neighbours (the own ones when the grid is a single slab), through peer mappings over NVLink, as they are
+    // produced.  Pointers are biased so that element idx of the own plane lands on the same node of the target plane;
+    // wrap = -1 / +1 where the neighbour is the periodic image across the ring of slabs (positions get -c / +c).  The
+    // kernel that follows on the stream (k_halo_xy_fused) announces the delivery to the neighbours and waits for theirs.
+    double *halo_lo[9];   // own plane 1   -> plane nzl' + 1 of the neighbour below   (x0 x1 x2 v0 v1 v2 g0 g1 g2 as written)
+    double *halo_hi[9];   // own plane nzl -> plane 0 of the neighbour above
+    double wrap_lo, wrap_hi;
+    int fused;
     const StepConsts *sc;
     double *partials;
 };
