@@ -123,9 +123,10 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_oracle_rate(grid, ensemble, model, steps, nthreads):
+def cpu_oracle_rate(grid, ensemble, model, steps, nthreads, target_seconds=None):
     """node-steps/s of the CPU oracle port (test infrastructure; here it is only the thing being TIMED as the
-    reported CPU baseline, never the product path)."""
+    reported CPU baseline, never the product path).  With target_seconds the step count is chosen from a two-step
+    pilot so that the timed run lasts about that long."""
     from oracle import oracle as orc
 
     system, vel = make_state(grid, explicit=True)
@@ -135,10 +136,14 @@ def cpu_oracle_rate(grid, ensemble, model, steps, nthreads):
     baro = dict(temp=p["temp"], press=p["press"], timecon=p["timecon_baro"], vel_press0=p["vel_press0"]) if p["baro"] else None
     md = o.md(system.pos, vel, system.masses, np.array(system.domain.rvecs), p["timestep"], thermo=thermo, baro=baro)
     md.run(1)
+    if target_seconds:
+        t0 = time.perf_counter()
+        md.run(2)
+        steps = int(min(2000, max(steps, np.ceil(target_seconds / max((time.perf_counter() - t0) / 2, 1e-6)))))
     t0 = time.perf_counter()
     md.run(steps)
     dt = time.perf_counter() - t0
-    return system.nnodes * steps / dt, dt
+    return system.nnodes * steps / dt, dt, steps
 
 
 def run_reference(args, rank, world):
@@ -146,7 +151,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    rate, dt = cpu_oracle_rate(args.cpu_grid, args.ensemble, args.model, args.steps, cores)
+    rate, dt, _ = cpu_oracle_rate(args.cpu_grid, args.ensemble, args.model, args.steps, cores)
     sample = "%d^3-cell fcu grid, %s, %d steps, OpenMP x%d (bounded sample of the %d^3 workload)" % (
         args.cpu_grid, args.ensemble.upper(), args.steps, cores, args.grid)
     line = {
@@ -330,8 +335,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        csteps = 3
-        rate, dt = cpu_oracle_rate(args.cpu_grid, args.ensemble, args.model, csteps, cores)
+        rate, dt, csteps = cpu_oracle_rate(args.cpu_grid, args.ensemble, args.model, 3, cores, target_seconds=12.0)
         cpu = {"value": rate, "unit": "node-steps/s", "cores": cores, "kind": "port",
                "sample": "%d^3-cell fcu grid, %s, %d steps, OpenMP x%d, %.1f s" % (args.cpu_grid, args.ensemble.upper(), csteps, cores, dt)}
 

@@ -211,8 +211,17 @@ k_peer_allreduce(const double *pc, int nbc, const double *pn, int nbn, const dou
                  int rank, PeerCtl *ctl, double *out) {
     __shared__ double mine[16];
     double a[7] = {0, 0, 0, 0, 0, 0, 0}, b[7] = {0, 0, 0, 0, 0, 0, 0}, c[1] = {0};
-    if (nbc > 0) partials_sum<7>(pc, nbc, kRedSlots, a);
-    if (nbn > 0) partials_sum<7>(pn, nbn, kRedSlots, b);
+    if (pn == pc + 7 && nbn == nbc && nbc > 1) {  // structured path: one coalesced pass over the 16-slot records
+        double all[16];
+        partials_sum16(pc, nbc, all);
+        for (int k = 0; k < 7; k++) {
+            a[k] = all[k];
+            b[k] = all[7 + k];
+        }
+    } else {
+        if (nbc > 0) partials_sum<7>(pc, nbc, kRedSlots, a);
+        if (nbn > 0) partials_sum<7>(pn, nbn, kRedSlots, b);
+    }
     if (nbd > 0) partials_sum<1>(pd, nbd, kRedSlots, c);
     if (threadIdx.x == 0) {
         for (int k = 0; k < 7; k++) {
@@ -474,8 +483,17 @@ int comm_allreduce(mm_handle *h, double *buf, int count) {
 __global__ void __launch_bounds__(256)
 k_sum_partials(const double *pc, int nbc, const double *pn, int nbn, const double *pd, int nbd, double *out) {
     double a[7] = {0, 0, 0, 0, 0, 0, 0}, b[7] = {0, 0, 0, 0, 0, 0, 0}, c[1] = {0};
-    if (nbc > 0) partials_sum<7>(pc, nbc, kRedSlots, a);
-    if (nbn > 0) partials_sum<7>(pn, nbn, kRedSlots, b);
+    if (pn == pc + 7 && nbn == nbc && nbc > 1) {  // structured path: one coalesced pass over the 16-slot records
+        double all[16];
+        partials_sum16(pc, nbc, all);
+        for (int k = 0; k < 7; k++) {
+            a[k] = all[k];
+            b[k] = all[7 + k];
+        }
+    } else {
+        if (nbc > 0) partials_sum<7>(pc, nbc, kRedSlots, a);
+        if (nbn > 0) partials_sum<7>(pn, nbn, kRedSlots, b);
+    }
     if (nbd > 0) partials_sum<1>(pd, nbd, kRedSlots, c);
     if (threadIdx.x == 0) {
         for (int k = 0; k < 7; k++) {

@@ -332,8 +332,17 @@ __global__ void __launch_bounds__(256)
 k_scalar(MDState *st, double *rvecs_dev, StepConsts *sc, unsigned ops, const double *pc, int nbc, const double *pn, int nbn,
          const double *pd, int nbd, double n3) {
     double fr[7] = {0, 0, 0, 0, 0, 0, 0}, kn[7] = {0, 0, 0, 0, 0, 0, 0}, dl[1] = {0};
-    if (ops & OP_TAKE_FORCE) partials_sum<7>(pc, nbc, kRedSlots, fr);
-    if ((ops & (OP_TAKE_KIN | OP_TAKE_FORCE)) && nbn > 0) partials_sum<7>(pn, nbn, kRedSlots, kn);
+    if (pn == pc + 7 && nbn == nbc && nbc > 1 && (ops & (OP_TAKE_KIN | OP_TAKE_FORCE))) {
+        double all[16];  // structured path: both halves live in the same 16-slot records
+        partials_sum16(pc, nbc, all);
+        for (int k = 0; k < 7; k++) {
+            fr[k] = all[k];
+            kn[k] = all[7 + k];
+        }
+    } else {
+        if (ops & OP_TAKE_FORCE) partials_sum<7>(pc, nbc, kRedSlots, fr);
+        if ((ops & (OP_TAKE_KIN | OP_TAKE_FORCE)) && nbn > 0) partials_sum<7>(pn, nbn, kRedSlots, kn);
+    }
     if ((ops & OP_TAKE_DELTA) && nbd > 0) partials_sum<1>(pd, nbd, kRedSlots, dl);
     // Work on a shared-memory copy of the state: the serial algebra below touches a few hundred fields, and as
     // dependent global-memory accesses they cost ~30 us per launch; from shared memory it is a few.
