@@ -285,18 +285,23 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     const int oslot = (row - 1) * OX + (lane - 1);
     if (TMA) {
         if (tid == 0) {
-            for (int st = 0; st < kStages; st++) mbar_init(smem_u32(&s_full[st]), NF);
+            for (int st = 0; st < kStages; st++) mbar_init(smem_u32(&s_full[st]), 1);
             mbar_fence_init();
         }
         __syncthreads();
     }
-    auto stage_issue = [&](const int q, const unsigned st) {  // plane q -> stage st
-        if (tid < NF) {
+    // plane q -> stage st.  ONE thread (lane 0 of the top apron row, whose own cells nobody uses) arms the barrier with the
+    // bytes of all NF boxes and issues them back to back; with one box per thread the compiler serialises the issuing
+    // lanes in an elected-lane loop that showed up with 6 % of the stall samples.
+    auto stage_issue = [&](const int q, const unsigned st) {
+        if (tid == (TY - 1) * TX) {
             const unsigned bar = smem_u32(&s_full[st]);
-            mbar_arrive_expect(bar, TY * kBoxW * 8u);
+            mbar_arrive_expect(bar, NF * TY * kBoxW * 8u);
             // node k0 - 1 of the tile is padded column 30 bx + 1; the box starts one column earlier (even)
-            tma_load_3d(smem_u32(s_stage) + (st * kStageDoubles + tid * (TY * kBoxW)) * 8u, &maps.in[tid], (int)(blockIdx.x * OX),
-                        (int)(blockIdx.y * OY), q, bar);
+#pragma unroll
+            for (int f = 0; f < NF; f++)
+                tma_load_3d(smem_u32(s_stage) + (st * kStageDoubles + f * (TY * kBoxW)) * 8u, &maps.in[f], (int)(blockIdx.x * OX),
+                            (int)(blockIdx.y * OY), q, bar);
         }
     };
     if (TMA) {

@@ -136,6 +136,52 @@ def test_matches_oracle_md_on_larger_grid(structured):
                 assert gio.rel_rms(thermo.chain.vel, md.chain_vel) <= 1e-7
 
 
+@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("ens", ["nve", "npt"])
+def test_structured_md_multitile_matches_indexed(ens, variant, monkeypatch):
+    """Fused marching kernel (register-prefetch and TMA variants) vs the indexed kernels on a grid that needs several
+    tiles in x (partial last tile, odd pitch), partial tiles in y and more than one chunk along z: 12 steps."""
+    from micmec_b200.system import System
+    from micmec_b200.celltypes import TYPE_FCU
+    from micmec_b200.pes.mmff import MicMecForceField, ForcePartMechanical
+    from micmec_b200.sampling.verlet import VerletIntegrator
+    from micmec_b200.sampling.nvt import NHCThermostat
+    from micmec_b200.sampling.npt import MTKBarostat, TBCombination
+    from micmec_b200.units import femtosecond, pascal
+
+    monkeypatch.setenv("MICMEC_B200_VARIANT", str(variant))
+    shape = (37, 11, 41)
+    rng = np.random.default_rng(21)
+    base = System.periodic_grid(shape, TYPE_FCU, explicit=True)
+    pos0 = base.pos + 0.2 * rng.standard_normal(base.pos.shape)
+    vel0 = 1e-5 * rng.standard_normal(base.pos.shape)
+    vel0 -= vel0.mean(axis=0)
+    runs = {}
+    for structured in (False, True):
+        system = base if not structured else System.periodic_grid(shape, TYPE_FCU, explicit=False)
+        system.pos[:] = pos0
+        mmf = MicMecForceField(system, [ForcePartMechanical(system, structured=structured)])
+        hooks = []
+        if ens == "npt":
+            thermo = NHCThermostat(300.0, timecon=100 * femtosecond, chain_vel0=np.array([1e-4, -2e-4, 5e-5]),
+                                   chain_pos0=np.zeros(3), restart=True)
+            baro = MTKBarostat(mmf, 300.0, 1e6 * pascal, timecon=1e5 * femtosecond,
+                               vel_press0=1e-6 * np.array([[1.0, 0.2, -0.1], [0.2, -0.5, 0.3], [-0.1, 0.3, 0.8]]), restart=True)
+            hooks = [TBCombination(thermo, baro)]
+        verlet = VerletIntegrator(mmf, timestep=10 * femtosecond, hooks=hooks, vel0=vel0.copy())
+        verlet.run(12)
+        runs[structured] = (verlet.pos.copy(), verlet.vel.copy(), verlet.gpos.copy(), verlet.econs, verlet.temp, verlet.press,
+                            np.array(verlet.mmf.system.domain.rvecs))
+    a, b = runs[False], runs[True]
+    assert gio.rel_rms(b[0], a[0]) <= 1e-11
+    assert gio.rel_rms(b[1], a[1]) <= 1e-9
+    assert gio.rel_rms(b[2], a[2]) <= 1e-9
+    assert abs(b[3] - a[3]) <= 1e-10 * abs(a[3])
+    assert abs(b[4] - a[4]) <= 1e-10 * a[4]
+    assert abs(b[5] - a[5]) <= 1e-8 * abs(a[5])
+    assert gio.rel_rms(b[6], a[6]) <= 1e-12
+
+
 class CountingHook(object):
     """A conventional hook as a user of the reference would write it."""
 
