@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tile-rows", type=int, default=0, help="tuning: warps per block of the marching kernel (8/12/16)")
-    ap.add_argument("--variant", type=int, default=-1, help="tuning bits of the marching kernel (1 pairwise barriers, 2 TMA loads, 4 two planes per trip, 8 TMA stores)")
+    ap.add_argument("--variant", type=int, default=-1, help="tuning bits of the marching kernel (1 pairwise barriers, 2 TMA loads, 4 two planes per trip, 8 one barrier per plane)")
     ap.add_argument("--chunk", type=int, default=0, help="tuning: planes per block along z")
     ap.add_argument("--generic", action="store_true", help="force the indexed-topology kernels (no structured path)")
     return ap.parse_args()

@@ -12,7 +12,6 @@ namespace mm {
 
 constexpr int TX = 32;  // lanes along x: one warp per tile row
 constexpr int kStages = 4;   // planes in flight in the staged (bulk-copy) variant
-constexpr int kOutField = 192;  // doubles per field of the output staging tile (30 x 6 owned nodes = 180, padded to 128-byte multiples)
 // MM_ABLATE (profiles/ablation.sh only, never in the product build): remove one ingredient of k_march to time the rest.
 // 1 no barriers, 2 no shared-memory exchange (and no barriers), 4 no cell arithmetic, 8 no shuffles, 16 no global stores,
 // 32 no global loads after the first plane.  Results are meaningless; only the launch time is looked at.
@@ -87,17 +86,6 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
                  "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-
-// shared memory -> one box of a rank-3 tensor map (bulk-group completion); parts of the box outside the array are dropped
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int c0, int c1, int c2, unsigned src) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                     reinterpret_cast<unsigned long long>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-// generic-proxy writes to shared memory -> visible to the async proxy (executed by the writers before the barrier)
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Delivery of one boundary-plane triple into a neighbour's halo plane (fused halo exchange).  Deliberately NOT inlined:
 // it runs for 2 of the planes of a slab, and as inlined predicated stores it costs every plane 18 address computations
@@ -187,7 +175,7 @@ __device__ __forceinline__ void scell_eval(const double Hs[9], const SParams &kp
 //   LEAN    no virial, kinetic-energy diagonal only (NVE / NVT steps whose pressure nobody looks at)
 //   VAR     tuning bits (measured in profiles/): 1 = neighbouring rows synchronise pairwise through named barriers instead
 //           of two block-wide barriers per plane; 2 = TMA loads (kStages planes in flight); 4 = two planes per trip;
-//           8 = with 2: TMA stores through a shared-memory tile
+//           8 = one synchronisation per plane (the gather of node plane p-2 is delayed by an iteration, see PIPE below)
 //   TY      tile rows (warps per block); the tile owns (TX-2) x (TY-2) node columns
 //
 // Loads (VAR & 2).  The ablation in profiles/ shows where the time of the register-prefetch kernel goes: removing the
@@ -209,12 +197,17 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     constexpr bool PSYNC = (VAR & 1) != 0;   // pairwise named-barrier handshakes instead of block barriers
     constexpr bool TMA = (VAR & 2) != 0;     // node data staged by bulk async copies (NST planes in flight), see below
     constexpr int UNR = (VAR & 4) ? 2 : 1;   // planes per loop trip
-    constexpr bool TST = TMA && (VAR & 8) != 0;  // results leave through a shared-memory tile and TMA stores (measured slower)
+    // PIPE: ONE block barrier per plane.  The gather of node plane p-2 (its second kick and stores) is delayed by an
+    // iteration: its shared-memory input was published before the barrier of iteration p, so the region between two
+    // barriers holds the exchange reads and shuffles of two planes, the stores of plane p-2 and the cell arithmetic of
+    // layer p-1 as independent instruction streams.  sf / sb are double-buffered by plane parity.
+    constexpr bool PIPE = (VAR & 8) != 0;
+    constexpr int NB = PIPE ? 2 : 1;
     constexpr int NF = STEP ? 11 : 3;        // staged fields per node: x (3) [, v (3), g (3), m, 1/m]
-    __shared__ double sf[3][TY][TX];  // forward exchange along y: position of the row above
-    __shared__ double sb[3][TY][TX];  // backward exchange along y: x-combined gradient part of the row below
+    __shared__ double sf[NB][3][TY][TX];  // forward exchange along y: position of the row above
+    __shared__ double sb[NB][3][TY][TX];  // backward exchange along y: x-combined gradient part of the row below
     __shared__ __align__(8) unsigned long long s_full[kStages];
-    extern __shared__ __align__(128) double s_stage[];  // TMA: [kStages][NF][TY][kBoxW], then the output tiles [2][9][kOutField]
+    extern __shared__ __align__(128) double s_stage[];  // TMA: [kStages][NF][TY][kBoxW]
 
     const int lane = threadIdx.x, row = threadIdx.y;
     const int nx = a.nx, ny = a.ny, nxp = a.nxp;
@@ -257,6 +250,8 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     double fpxy[3] = {0, 0, 0}, fdxy[3] = {0, 0, 0}, fpyd[3] = {0, 0, 0};  // forward: xy-combined sums / differences
     double Dp[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};                            // D' of the previous cell layer
     double vh[3] = {0, 0, 0}, mprev = 0.0, hminv_prev = 0.0;  // STEP: half-kicked velocity / mass of the previous plane
+    double vh2[3] = {0, 0, 0}, m2 = 0.0, hm2 = 0.0;           // PIPE: ... of the plane before that
+    double gdc[3] = {0, 0, 0};                                 // PIPE: own-row gradient part of node plane p-2
 
     // software pipeline: raw loads of the NEXT plane are issued before the arithmetic of the current one (the arrays
     // carry one spare plane, so the prefetch of the last iteration stays inside the allocation)
@@ -278,11 +273,6 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     const int tid = row * TX + lane;
     unsigned it = 0;  // planes done: plane p = c0 - 1 + it lives in stage it % kStages, barrier phase (it / kStages) & 1
     constexpr unsigned kStageDoubles = NF * TY * kBoxW;
-    // output tile (staged variant): the owned 30 x 6 nodes of a plane, dense rows of 30 (the box of the store descriptors),
-    // two copies by plane parity.  The threads of the owned lanes / rows write their node, the async proxy stores the box.
-    double *const s_out = s_stage + kStages * kStageDoubles;
-    const bool in_box = lane >= 1 && lane <= OX && row >= 1 && row <= OY;
-    const int oslot = (row - 1) * OX + (lane - 1);
     if (TMA) {
         if (tid == 0) {
             for (int st = 0; st < kStages; st++) mbar_init(smem_u32(&s_full[st]), 1);
@@ -311,12 +301,50 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
         issue_loads(idx);
     }
 
+    // Completion of node plane q: gradient = row-below part (shared memory, published before the last barrier) + own part,
+    // second kick (verlet.py:152-153), kinetic moments, stores (and delivery to the neighbour slab when q is a boundary plane)
+    auto finish_node = [&](auto halo_tag, const int sbpar, const unsigned at, const int q, const double (&vhq)[3], const double hmq,
+                           const double mq, const double (&gdq)[3]) {
+        constexpr bool HALO = decltype(halo_tag)::value;
+        double g[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) g[j] = ((MM_ABLATE & 2) ? gdq[j] * 1.25 : sb[sbpar][j][rowm][lane]) + gdq[j];
+        if (STEP) {
+            double vn[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                vn[j] = fma(-hmq, g[j], vhq[j]);
+                st_if(own_xy, a.vo[j] + at, vn[j]);
+            }
+            if (HALO && a.fused && q == 1) deliver3(a.halo_lo[3], a.halo_lo[4], a.halo_lo[5], at, own_xy, vn[0], vn[1], vn[2]);
+            if (HALO && a.fused && q == a.nzl) deliver3(a.halo_hi[3], a.halo_hi[4], a.halo_hi[5], at, own_xy, vn[0], vn[1], vn[2]);
+            const double mo = own_xy ? mq : 0.0;
+            const double mx = mo * vn[0], my = mo * vn[1], mz = mo * vn[2];
+            acc[7] = fma(mx, vn[0], acc[7]);
+            acc[8] = fma(my, vn[1], acc[8]);
+            acc[9] = fma(mz, vn[2], acc[9]);
+            if (!LEAN) {
+                acc[10] = fma(my, vn[2], acc[10]);
+                acc[11] = fma(mx, vn[2], acc[11]);
+                acc[12] = fma(mx, vn[1], acc[12]);
+            }
+        }
+        const bool pg = own_xy && write_g;
+#pragma unroll
+        for (int j = 0; j < 3; j++) st_if(pg, a.go[j] + at, g[j]);
+        if (HALO && a.fused && q == 1) deliver3(a.halo_lo[6], a.halo_lo[7], a.halo_lo[8], at, pg, g[0], g[1], g[2]);
+        if (HALO && a.fused && q == a.nzl) deliver3(a.halo_hi[6], a.halo_hi[7], a.halo_hi[8], at, pg, g[0], g[1], g[2]);
+        if (!LEAN) acc[13] += own_xy ? fma(g[0], g[0], fma(g[1], g[1], g[2] * g[2])) : 0.0;
+    };
+
     // One plane.  CELL: cell layer p-1 (planes p-1 and p) exists; NODE: node plane p-1 (cell layers p-2, p-1) is
     // completed.  The first two planes of a chunk are peeled (CELL / NODE false), so that the steady-state loop has no
     // uniform branches and its constant loads stay on the uniform datapath.
-    auto plane_body = [&](auto cell_tag, auto node_tag, auto halo_tag, const int p) {
+    auto plane_body = [&](auto cell_tag, auto node_tag, auto gath_tag, auto halo_tag, const int p) {
         constexpr bool CELL = decltype(cell_tag)::value, NODE = decltype(node_tag)::value;
+        constexpr bool GATH = decltype(gath_tag)::value;  // PIPE: node plane p-2 is completed in this iteration
         constexpr bool HALO = decltype(halo_tag)::value;  // this plane may be a boundary plane of the slab (fused halo)
+        const int par = PIPE ? (p & 1) : 0;
         double cx0, cx1, cx2, cv[3] = {0, 0, 0}, cg[3] = {0, 0, 0}, cm = 0.0, cminv = 0.0;
         const unsigned st = it % kStages;
         if (TMA) {
@@ -377,12 +405,7 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             }
         }
         if ((STEP || ROT == 2) && CELL) {
-            if (TST) {
-                if (in_box) {
-#pragma unroll
-                    for (int j = 0; j < 3; j++) s_out[((p & 1) * 9 + j) * kOutField + oslot] = r[j];
-                }
-            } else {
+            {
                 const bool px = own_xy && p < c1;
 #pragma unroll
                 for (int j = 0; j < 3; j++) st_if(px, a.xo[j] + idx, r[j]);
@@ -394,38 +417,23 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
                              fma(a.wrap_hi, cw[1], r[1]), fma(a.wrap_hi, cw[2], r[2]));
             }
         }
-        if (TST) fence_async_smem();  // the tile parts written since the last barrier (x of plane p; v, g of plane p-2)
 
         // ---- forward butterfly: y through shared memory, x by shuffle, z in registers -------------------------------
 #pragma unroll
         for (int j = 0; j < 3; j++)
-            if (!(MM_ABLATE & 2)) sf[j][row][lane] = r[j];
+            if (!(MM_ABLATE & 2)) sf[par][j][row][lane] = r[j];
         if (MM_ABLATE & 3) {
-        } else if (PSYNC) {  // row r only needs row r+1: producer arrives, consumer waits (barrier ids 1 .. TY-1)
+        } else if (PSYNC && !PIPE) {  // row r only needs row r+1: producer arrives, consumer waits (barrier ids 1 .. TY-1)
             if (row > 0) bar_arrive(row, 2 * TX);
             if (row + 1 < TY) bar_wait(row + 1, 2 * TX);
         } else {
             __syncthreads();
         }
         if (TMA && !(MM_ABLATE & 32) && p + kStages <= c1) stage_issue(p + kStages, st);  // all threads have read stage st
-        if (TST) {  // warp 1 stores: x of plane p (tile p & 1), v and g of node plane p-2 (written at the end of iteration p-1)
-            const int f = tid - TX;
-            if (f >= 0 && f < 9) {
-                const bool xs_ok = (STEP || ROT == 2) && CELL && p < c1;
-                const bool vg_ok = p >= c0 + 2 && (f < 6 ? STEP != 0 : write_g != 0);
-                if (f < 3 ? xs_ok : vg_ok) {
-                    const int q = f < 3 ? p : p - 2;
-                    tma_store_3d(&maps.out[f], (int)(blockIdx.x * OX) + kGhostX, (int)(blockIdx.y * OY) + 1, q,
-                                 smem_u32(s_out + (((f < 3 ? p : p - 1) & 1) * 9 + f) * kOutField));
-                }
-                tma_store_commit();
-                tma_store_wait_read<1>();  // the group of iteration p-1 has read its tile: safe to rewrite after the next barrier
-            }
-        }
         double pxy[3], dxy[3], pyd[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-            const double rn = (MM_ABLATE & 2) ? r[j] * 1.25 : sf[j][rowp][lane];
+            const double rn = (MM_ABLATE & 2) ? r[j] * 1.25 : sf[par][j][rowp][lane];
             const double py = rn + r[j], dy = rn - r[j];
             const double pyn = (MM_ABLATE & 8) ? py * 1.5 : __shfl_down_sync(0xffffffffu, py, 1);
             const double dyn = (MM_ABLATE & 8) ? dy * 0.75 : __shfl_down_sync(0xffffffffu, dy, 1);
@@ -433,6 +441,8 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
             dxy[j] = pyn - py;   // x difference of the y sums
             pyd[j] = dy + dyn;   // y difference of the x sums
         }
+
+        if (PIPE && GATH) finish_node(halo_tag, par ^ 1, idx - 2 * plane, p - 2, vh2, hm2, m2, gdc);
 
         double D[9];
         if (CELL) {
@@ -482,60 +492,28 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
                 const double s02m = (MM_ABLATE & 8) ? (p0 + p2) * 1.5 : __shfl_up_sync(0xffffffffu, p0 + p2, 1);
                 const double p1m = (MM_ABLATE & 8) ? p1 * 0.75 : __shfl_up_sync(0xffffffffu, p1, 1);
                 const double ya = s02m + (p2 - p0), yb = p1m + p1;
-                if (!(MM_ABLATE & 2)) sb[j][row][lane] = ya + yb;
+                if (!(MM_ABLATE & 2)) sb[par][j][row][lane] = ya + yb;
                 gd[j] = ya - yb;
             }
         }
-        if (MM_ABLATE & 3) {
-        } else if (PSYNC) {  // row r only needs row r-1 (barrier ids TY .. 2 TY - 2); these two handshakes per plane also order
-                      // the reuse of sf / sb between planes
-            if (row + 1 < TY) bar_arrive(TY + row, 2 * TX);
-            if (row > 0) bar_wait(TY + row - 1, 2 * TX);
-        } else {
-            __syncthreads();
-        }
-        if (NODE) {
-            double g[3];
-#pragma unroll
-            for (int j = 0; j < 3; j++) g[j] = ((MM_ABLATE & 2) ? gd[j] * 1.25 : sb[j][rowm][lane]) + gd[j];
-            const unsigned at = idx - plane;
-            if (STEP) {  // second kick (verlet.py:152-153) + kinetic moments of the new velocities
-                double vn[3];
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    vn[j] = fma(-hminv_prev, g[j], vh[j]);
-                    if (TST) {
-                        if (in_box) s_out[((p & 1) * 9 + 3 + j) * kOutField + oslot] = vn[j];
-                    } else {
-                        st_if(own_xy, a.vo[j] + at, vn[j]);
-                    }
-                }
-                if (HALO && !TST && a.fused && p == 2) deliver3(a.halo_lo[3], a.halo_lo[4], a.halo_lo[5], at, own_xy, vn[0], vn[1], vn[2]);
-                if (HALO && !TST && a.fused && p == a.nzl + 1) deliver3(a.halo_hi[3], a.halo_hi[4], a.halo_hi[5], at, own_xy, vn[0], vn[1], vn[2]);
-                const double mo = own_xy ? mprev : 0.0;
-                const double mx = mo * vn[0], my = mo * vn[1], mz = mo * vn[2];
-                acc[7] = fma(mx, vn[0], acc[7]);
-                acc[8] = fma(my, vn[1], acc[8]);
-                acc[9] = fma(mz, vn[2], acc[9]);
-                if (!LEAN) {
-                    acc[10] = fma(my, vn[2], acc[10]);
-                    acc[11] = fma(mx, vn[2], acc[11]);
-                    acc[12] = fma(mx, vn[1], acc[12]);
-                }
-            }
-            if (TST) {
-                if (in_box) {
-#pragma unroll
-                    for (int j = 0; j < 3; j++) s_out[((p & 1) * 9 + 6 + j) * kOutField + oslot] = g[j];
-                }
+        if (!PIPE) {
+            if (MM_ABLATE & 3) {
+            } else if (PSYNC) {  // row r only needs row r-1 (barrier ids TY .. 2 TY - 2); these two handshakes per plane also
+                          // order the reuse of sf / sb between planes
+                if (row + 1 < TY) bar_arrive(TY + row, 2 * TX);
+                if (row > 0) bar_wait(TY + row - 1, 2 * TX);
             } else {
-                const bool pg = own_xy && write_g;
-#pragma unroll
-                for (int j = 0; j < 3; j++) st_if(pg, a.go[j] + at, g[j]);
-                if (HALO && a.fused && p == 2) deliver3(a.halo_lo[6], a.halo_lo[7], a.halo_lo[8], at, pg, g[0], g[1], g[2]);
-                if (HALO && a.fused && p == a.nzl + 1) deliver3(a.halo_hi[6], a.halo_hi[7], a.halo_hi[8], at, pg, g[0], g[1], g[2]);
+                __syncthreads();
             }
-            if (!LEAN) acc[13] += own_xy ? fma(g[0], g[0], fma(g[1], g[1], g[2] * g[2])) : 0.0;
+            if (NODE) finish_node(halo_tag, 0, idx - plane, p - 1, vh, hminv_prev, mprev, gd);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                gdc[j] = gd[j];
+                vh2[j] = vh[j];
+            }
+            m2 = mprev;
+            hm2 = hminv_prev;
         }
         if (CELL) {
 #pragma unroll
@@ -555,26 +533,26 @@ k_march(const __grid_constant__ SParams kp, const __grid_constant__ MarchArgs a,
     // first three and the last two iterations of a chunk: only those bodies carry the delivery code of the fused halo.
     constexpr std::true_type T{};
     constexpr std::false_type F{};
-    plane_body(F, F, T, c0 - 1);
-    plane_body(T, F, T, c0);
-    plane_body(T, T, T, c0 + 1);
+    plane_body(F, F, F, T, c0 - 1);
+    plane_body(T, F, F, T, c0);
+    if (!PIPE) {
+        plane_body(T, T, T, T, c0 + 1);
 #pragma unroll UNR
-    for (int p = c0 + 2; p <= c1 - 2; p++) plane_body(T, T, F, p);
+        for (int p = c0 + 2; p <= c1 - 2; p++) plane_body(T, T, T, F, p);
 #pragma unroll 1
-    for (int p = max(c0 + 2, c1 - 1); p <= c1; p++) plane_body(T, T, T, p);
-
-    if (TST) {  // drain: v and g of node plane c1-1 were written at the end of iteration c1 (tile c1 & 1)
-        fence_async_smem();
+        for (int p = max(c0 + 2, c1 - 1); p <= c1; p++) plane_body(T, T, T, T, p);
+    } else {
+        plane_body(T, T, F, T, c0 + 1);
+        if (c0 + 2 <= c1) plane_body(T, T, T, T, c0 + 2);  // completes node plane c0 (the lower boundary plane of the first chunk)
+#pragma unroll UNR
+        for (int p = c0 + 3; p <= c1 - 2; p++) plane_body(T, T, T, F, p);
+#pragma unroll 1
+        for (int p = max(c0 + 3, c1 - 1); p <= c1; p++) plane_body(T, T, T, T, p);
+        // drain: node plane c1-1 (its row-below part was published in iteration c1; after the rotation vh2 / gdc are its data)
         __syncthreads();
-        const int f = tid - TX;
-        if (f >= 3 && f < 9) {
-            if (c1 >= c0 + 1 && (f < 6 ? STEP != 0 : write_g != 0))
-                tma_store_3d(&maps.out[f], (int)(blockIdx.x * OX) + kGhostX, (int)(blockIdx.y * OY) + 1, c1 - 1,
-                             smem_u32(s_out + ((c1 & 1) * 9 + f) * kOutField));
-            tma_store_commit();
-        }
-        if (f >= 0 && f < 9) tma_store_wait_read<0>();
+        finish_node(T, c1 & 1, idx - 2 * plane, c1 - 1, vh2, hm2, m2, gdc);
     }
+
     if (SINGLE && own_xy) acc[0] = fma((double)(c1 - c0), kp.st[0].efree, acc[0]);
     // block reduction: warp shuffles, then one warp over the per-warp sums
     __shared__ double red[TY][14];

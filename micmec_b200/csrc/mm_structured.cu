@@ -340,13 +340,6 @@ static int sg_encode_maps(mm_handle *h) {
     for (int c = 0; c < 2; c++)
         for (int d = 0; d < 3; d++) ok = ok && one(&g.tm_x[c][d], g.x[c][d]) && one(&g.tm_v[c][d], g.v[c][d]) && one(&g.tm_g[c][d], g.g[c][d]);
     ok = ok && one(&g.tm_m, g.m) && one(&g.tm_minv, g.minv);
-    const cuuint32_t sbox[3] = {(cuuint32_t)(TX - 2), (cuuint32_t)(g.tile_rows - 2), 1};
-    auto store = [&](CUtensorMap *m, double *p) {
-        return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p, dims, strides, sbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-    };
-    for (int c = 0; c < 2; c++)
-        for (int d = 0; d < 3; d++) ok = ok && store(&g.ts_x[c][d], g.x[c][d]) && store(&g.ts_v[c][d], g.v[c][d]) && store(&g.ts_g[c][d], g.g[c][d]);
     return ok ? MM_OK : MM_ERR_CUDA;
 }
 
@@ -574,7 +567,7 @@ static int launch_one(mm_handle *h, const MarchArgs &a, int write_g) {
     sg_blocks(h, grid);
     prof_begin(h, STEP);
     // staged variant: kStages planes of the tile in dynamic shared memory (opt-in above 48 KB, once per instantiation)
-    constexpr size_t dyn = (VAR & 2) ? sizeof(double) * (kStages * (STEP ? 11 : 3) * TY * kBoxW + 2 * 9 * kOutField) : 0;
+    constexpr size_t dyn = (VAR & 2) ? sizeof(double) * (kStages * (STEP ? 11 : 3) * TY * kBoxW) : 0;
     if (dyn > 0) {
         static bool configured[64] = {false};
         if (!configured[h->device & 63]) {
@@ -592,13 +585,6 @@ static int launch_one(mm_handle *h, const MarchArgs &a, int write_g) {
         }
         maps.in[9] = g.tm_m;
         maps.in[10] = g.tm_minv;
-        // what the launch writes: the other x / v sets; the gradient goes where a.go points (FORCE: current set, STEP: other)
-        const int gx = g.cx ^ 1, gv = g.cv ^ 1, gg = (a.go[0] == g.g[g.cg][0]) ? g.cg : (g.cg ^ 1);
-        for (int d = 0; d < 3; d++) {
-            maps.out[d] = g.ts_x[gx][d];
-            maps.out[3 + d] = g.ts_v[gv][d];
-            maps.out[6 + d] = g.ts_g[gg][d];
-        }
     } else {
         memset(&maps, 0, sizeof(maps));
     }
@@ -632,14 +618,14 @@ static int launch_march(mm_handle *h, const MarchArgs &a, bool step, int rot, in
     const bool stageable = h->sg.tma_ok != 0;  // tensor maps encoded (sg_setup)
     int var = h->sg.variant & 15;
     if (!stageable) var &= ~2;
-    if (var & 2) var &= ~1;  // the refill of a stage relies on the block barrier
-    if (!(var & 2) || h->sg.fused) var &= ~8;
+    if (var & (2 | 8)) var &= ~1;  // the refill of a stage (and the one-barrier pipeline) rely on the block barrier
     switch (var) {  // tuning variants kept for the measurements in profiles/ (bits: see k_march)
         case 1: return launch_sel<true, 1>(h, a, step, rot, vm, lean, write_g);
         case 2: return launch_sel<true, 2>(h, a, step, rot, vm, lean, write_g);
         case 4: return launch_sel<true, 4>(h, a, step, rot, vm, lean, write_g);
         case 5: return launch_sel<true, 5>(h, a, step, rot, vm, lean, write_g);
         case 6: return launch_sel<true, 6>(h, a, step, rot, vm, lean, write_g);
+        case 8: return launch_sel<true, 8>(h, a, step, rot, vm, lean, write_g);
         case 10: return launch_sel<true, 10>(h, a, step, rot, vm, lean, write_g);
         case 14: return launch_sel<true, 14>(h, a, step, rot, vm, lean, write_g);
         default: return launch_sel<true, 0>(h, a, step, rot, vm, lean, write_g);

@@ -61,7 +61,6 @@ struct SGrid {
     uint8_t *type = nullptr;
     int cx = 0, cv = 0, cg = 0;     // which copy is current
     CUtensorMap tm_x[2][3], tm_v[2][3], tm_g[2][3], tm_m, tm_minv;  // load descriptors of the arrays above
-    CUtensorMap ts_x[2][3], ts_v[2][3], ts_g[2][3];                  // store descriptors
     int tma_ok = 0;                 // descriptors encoded (driver entry point available, pitch constraints met)
     // fused halo (see MarchArgs): where the z neighbours' copies of this slab's arrays live (own block when there is one
     // slab), their plane counts, and what the last marching launch already delivered
@@ -80,7 +79,8 @@ struct SGrid {
     double *d_partials = nullptr;   // [nblocks][kRedSlots]
     int nblocks = 0, nblocks_alloc = 0;
     int tile_rows = 8;              // TY of the marching kernel (warps per block)
-    int variant = 2;                // tuning bits of the marching kernel (k_march VAR); default: TMA loads
+    int variant = 14;               // tuning bits of the marching kernel (k_march VAR); default: TMA loads, one barrier
+                                    // per plane, two planes per loop trip
     int chunk = 32;                 // owned planes per block along z
     SParams sp;
 };
@@ -89,7 +89,6 @@ struct SGrid {
 // a padded plane; coordinates outside the array read as zero (the partial tiles at the upper x / y edge)
 struct alignas(64) TmaMaps {
     CUtensorMap in[11];  // x0 x1 x2 v0 v1 v2 g0 g1 g2 m 1/m
-    CUtensorMap out[9];  // x0 x1 x2 v0 v1 v2 g0 g1 g2 of the sets the launch writes; box = the (TX-2) x (TY-2) owned nodes
 };
 
 struct MarchArgs {
