@@ -35,8 +35,8 @@ BYTES_PER_NODE_EVAL = 52.0    # force-only evaluation: pos 24 + 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--ensemble", default="npt", choices=["nve", "nvt", "npt"])
     ap.add_argument("--model", default="original", choices=["original", "default"])
@@ -112,7 +112,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(name)
                 except Exception:
                     pass
-                self._stop_evt.wait(0.05)
+                self._stop_evt.wait(0.01)
         except Exception as exc:  # pragma: no cover
             self.reasons.add("unavailable: %s" % exc)
 
@@ -166,13 +166,20 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def workload_config(args, world):
+COMM_MODES = {
+    0: "NCCL send/recv halo planes + NCCL all-reduce of 16 doubles",
+    1: "halo planes stored into the neighbours' inboxes over NVLink peer memory + one-kernel mailbox all-reduce",
+    2: "fused halo: k_march stores its boundary planes into the neighbours' halo planes over NVLink peer memory + one-kernel mailbox all-reduce",
+}
+
+
+def workload_config(args, world, comm_mode=None):
     return {
         "workload": "synthetic %dx%dx%d-cell fcu grid %s MD (%s), dt 10 fs" % (
             args.grid, args.grid, args.grid, args.ensemble.upper(),
             {"nve": "velocity Verlet", "nvt": "NHC thermostat", "npt": "NHC thermostat + MTK barostat"}[args.ensemble]),
         "nodes_total": args.grid ** 3, "nodes_per_gpu": args.grid ** 3 // world, "force_evals_per_step": FORCE_EVALS[args.ensemble], "model": args.model,
-        "parallelism": "single GPU" if world == 1 else "%d z-slabs (one per GPU), NCCL halo planes + 16-double all-reduce" % world,
+        "parallelism": "single GPU" if world == 1 else "%d z-slabs (one per GPU); %s" % (world, COMM_MODES.get(comm_mode, "CPU arm: no exchange")),
         "cache": "inputs larger than L2 (pos/vel/gpos %.0f MB each)" % (24.0 * args.grid ** 3 / 1e6),
     }
 
@@ -229,8 +236,10 @@ def main():
     mmf = MicMecForceField(system, [part])
     stream = torch.cuda.Stream(device=local_rank)
     _lib.check(lib.mm_set_stream(part.handle, ctypes.c_void_p(stream.cuda_stream)))
+    comm_mode = None
     if world > 1:
         slabmod.init_comm(part, layout)
+        comm_mode = int(lib.mm_comm_mode(part.handle))
     hooks = []
     thermo = baro = None
     if p["thermo"]:
@@ -293,8 +302,17 @@ def main():
     else:
         kernel_ms, name, bpn = tot[0] / max(nl[0], 1), "k_cells (per-cell force kernel, indexed topology)", BYTES_PER_NODE_EVAL
     achieved = bpn * nnodes / (kernel_ms * 1e-3) / 1e9
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this grid (single GPU), if any
+    traffic = None
+    try:
+        caps = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        cap = caps.get("%s@%d" % ("k_march_step" if fused else "k_cells", args.grid))
+        if cap and world == 1:
+            traffic = float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])
+    except Exception:
+        pass
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "kernel": name, "bytes_per_node": bpn, "kernel_ms": kernel_ms, "launches_timed": int(nl[1] if fused else nl[0]),
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
         # whole step against the survey's convention of 108 B per node and force evaluation
@@ -344,7 +362,7 @@ def main():
             "metric": "MD node-steps/s (force+Verlet, fp64)", "value": value, "unit": "node-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "config": workload_config(args, world, comm_mode), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
             "force_evals_per_s": value * FORCE_EVALS[args.ensemble],
             "check": {"temp_K": scal[_lib.S_TEMP], "epot": scal[_lib.S_EPOT], "cons_err": scal[_lib.S_CONS_ERR]},

@@ -130,6 +130,9 @@ int mm_get_replica_results(mm_handle *h, double *energies_host /* [nreplicas] */
 int mm_comm_unique_id(const char *nccl_path, char *out128);
 int mm_comm_init(mm_handle *h, const char *nccl_path, const char *id128);
 int mm_comm_destroy(mm_handle *h);
+/* exchange mode the ranks agreed on: -1 no communicator, 0 NCCL send/recv + all-reduce, 1 peer inboxes over NVLink
+ * (CUDA IPC), 2 fused halo (the marching kernel stores its boundary planes into the neighbours' halo planes) */
+int mm_comm_mode(const mm_handle *h);
 
 /* ---- Domain  (micmec/pes/ext.pyx:36-123 + micmec/pes/domain.c:13-71) ------------------------------------ */
 /* rvecs [nvec][3]; writes volume (domain.c:23-48) and the reciprocal vectors gvecs [nvec][3] (ext.pyx:64-71) */

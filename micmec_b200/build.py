@@ -10,7 +10,7 @@ LIB = os.path.join(HERE, "libmicmec_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
-    "-Xcompiler", "-fPIC", "-shared", "--fmad=true", "-Xptxas", "-v",
+    "-Xcompiler", "-fPIC", "-shared", "--fmad=true", "-Xptxas", "-v", "--threads", "0",
 ]
 
 

@@ -559,6 +559,12 @@ int mm_comm_init(mm_handle *h, const char *nccl_path, const char *id128) {
     return peer_setup(h);
 }
 
+int mm_comm_mode(const mm_handle *h) {
+    if (!h || !h->comm) return -1;
+    if (!h->peer_mode) return 0;
+    return h->sg.fused ? 2 : 1;
+}
+
 int mm_comm_destroy(mm_handle *h) {
     if (h && h->comm && g_nccl.CommDestroy) {
         g_nccl.CommDestroy((ncclComm_t)h->comm);
