@@ -1,19 +1,204 @@
-"""Nose-Hoover chain thermostat (micmec/sampling/nvt.py:361-532) for the device-resident integrator.
+"""Thermostats: the Nose-Hoover chain (micmec/sampling/nvt.py:361-532) of the device-resident integrator, and
+host-driven Andersen / Berendsen / Langevin / CSVR / GLE hooks (nvt.py:48-358).
 
 ``NHChain`` holds the chain state on the host (positions, velocities, masses) exactly like the reference; the
 chain *propagation* of ``NHChain.__call__`` (nvt.py:410-451) runs inside the scalar kernel of libmicmec_b200.so and
 this object is refreshed from the device whenever the host needs it.  ``NHChain.__call__`` is kept as a plain
 NumPy method too, because the host-driven compatibility mode of ``VerletIntegrator`` (arbitrary Python hooks)
 calls thermostats the way the reference does.
+
+The other thermostats act on the host arrays of ``VerletIntegrator`` in its host-driven mode (every force
+evaluation still runs on the GPU through ``mmf.compute``).  They draw from the legacy global NumPy RNG with the
+same calls in the same order as the reference, so a seeded run reproduces the reference's trajectory exactly
+(tests/test_hooks_cpu.py, tests/test_hooks_gpu.py).
 """
 import numpy as np
 
 from ..units import boltzmann, femtosecond
 from .iterative import StateItem
-from .utils import clean_momenta, get_ndof_internal_md
+from .utils import clean_momenta, get_ndof_internal_md, get_random_vel, stabilized_cholesky_decomp
 from .verlet import VerletHook
 
-__all__ = ["NHChain", "NHCThermostat", "NHCAttributeStateItem"]
+__all__ = [
+    "AndersenThermostat", "BerendsenThermostat", "LangevinThermostat", "CSVRThermostat", "GLEThermostat",
+    "NHChain", "NHCThermostat", "NHCAttributeStateItem",
+]
+
+
+def _clean(iterative):
+    clean_momenta(iterative.pos, iterative.vel, iterative.masses, iterative.mmf.system.domain)
+
+
+def _default_ndof(iterative):
+    if iterative.ndof is None:
+        iterative.ndof = get_ndof_internal_md(iterative.pos.shape[0], iterative.mmf.system.domain.nvec)
+
+
+class AndersenThermostat(VerletHook):
+    """Velocities redrawn from the Maxwell-Boltzmann distribution every call (nvt.py:48-107)."""
+
+    name = "Andersen"
+    kind = "stochastic"
+    method = "thermostat"
+
+    def __init__(self, temp, start=0, step=1, select=None, annealing=1.0):
+        self.temp = temp
+        self.select = select
+        self.annealing = annealing
+        VerletHook.__init__(self, start, step)
+        self.start, self.step = start, step  # kept for callers that inspect them; Verlet hooks fire every step
+
+    def init(self, iterative):
+        _clean(iterative)
+
+    def pre(self, iterative, G1_add=None):
+        before = iterative._compute_ekin()
+        if self.select is None:
+            iterative.vel[:] = get_random_vel(self.temp, False, iterative.masses)
+        else:
+            iterative.vel[self.select] = get_random_vel(self.temp, False, iterative.masses, self.select)
+        _clean(iterative)
+        self.econs_correction += before - iterative._compute_ekin()
+        self.temp *= self.annealing
+
+    def post(self, iterative, G1_add=None):
+        pass
+
+
+class BerendsenThermostat(VerletHook):
+    """Weak-coupling velocity rescaling (nvt.py:110-162)."""
+
+    name = "Berendsen"
+    kind = "deterministic"
+    method = "thermostat"
+
+    def __init__(self, temp, start=0, timecon=100 * femtosecond, restart=False):
+        self.temp = temp
+        self.timecon = timecon
+        self.restart = restart
+        VerletHook.__init__(self, start, 1)
+
+    def init(self, iterative):
+        if not self.restart:
+            _clean(iterative)
+        _default_ndof(iterative)
+
+    def pre(self, iterative, G1_add=None):
+        ekin = iterative.ekin
+        temp_now = 2.0 * ekin / (boltzmann * iterative.ndof)
+        scale = np.sqrt(1 + iterative.timestep / self.timecon * (self.temp / temp_now - 1))
+        iterative.vel[:] = scale * iterative.vel
+        iterative.ekin = iterative._compute_ekin()
+        self.econs_correction += (1 - scale ** 2) * ekin
+
+    def post(self, iterative, G1_add=None):
+        pass
+
+
+class LangevinThermostat(VerletHook):
+    """Half-step Ornstein-Uhlenbeck velocity update before and after the Verlet step (nvt.py:165-218); this is the
+    thermostat ``simulations/md.py`` uses."""
+
+    name = "Langevin"
+    kind = "stochastic"
+    method = "thermostat"
+
+    def __init__(self, temp, start=0, timecon=100 * femtosecond):
+        self.temp = temp
+        self.timecon = timecon
+        VerletHook.__init__(self, start, 1)
+
+    def init(self, iterative):
+        _clean(iterative)
+
+    def _half_step(self, iterative):
+        before = iterative.ekin
+        damp = np.exp(-iterative.timestep / self.timecon / 2)
+        kick = np.sqrt((1.0 - damp ** 2) * self.temp * boltzmann / iterative.masses).reshape(-1, 1)
+        iterative.vel[:] = damp * iterative.vel + kick * np.random.normal(0, 1, iterative.vel.shape)
+        iterative.ekin = iterative._compute_ekin()
+        self.econs_correction += before - iterative.ekin
+
+    def pre(self, iterative, G1_add=None):
+        self._half_step(iterative)
+
+    def post(self, iterative, G1_add=None):
+        self._half_step(iterative)
+
+    thermo = _half_step
+
+
+class CSVRThermostat(VerletHook):
+    """Canonical sampling through stochastic velocity rescaling (nvt.py:221-274)."""
+
+    name = "CSVR"
+    kind = "stochastic"
+    method = "thermostat"
+
+    def __init__(self, temp, start=0, timecon=100 * femtosecond):
+        self.temp = temp
+        self.timecon = timecon
+        VerletHook.__init__(self, start, 1)
+
+    def init(self, iterative):
+        _clean(iterative)
+        _default_ndof(iterative)
+        self.kin = 0.5 * iterative.ndof * boltzmann * self.temp
+
+    def pre(self, iterative, G1_add=None):
+        decay = np.exp(-iterative.timestep / self.timecon)
+        first = np.random.normal(0, 1)
+        rest = (np.random.normal(0, 1, iterative.ndof - 1) ** 2).sum()
+        iterative.ekin = iterative._compute_ekin()
+        fact = (1 - decay) * self.kin / iterative.ndof / iterative.ekin
+        alpha = np.sign(first + np.sqrt(decay / fact)) * np.sqrt(
+            decay + (rest + first ** 2) * fact + 2 * first * np.sqrt(decay * fact))
+        iterative.vel[:] = alpha * iterative.vel
+        iterative.ekin_new = alpha ** 2 * iterative.ekin
+        self.econs_correction += (1 - alpha ** 2) * iterative.ekin
+        iterative.ekin = iterative.ekin_new
+
+    def post(self, iterative, G1_add=None):
+        pass
+
+
+class GLEThermostat(VerletHook):
+    """Coloured-noise (generalised Langevin) thermostat with ``ns`` auxiliary momenta per coordinate (nvt.py:277-358)."""
+
+    name = "GLE"
+    kind = "stochastic"
+    method = "thermostat"
+
+    def __init__(self, temp, a_p, c_p=None, start=0):
+        self.temp = temp
+        self.ns = int(a_p.shape[0] - 1)
+        self.a_p = a_p
+        self.c_p = boltzmann * temp * np.eye(self.ns + 1) if c_p is None else c_p
+        VerletHook.__init__(self, start, 1)
+
+    def init(self, iterative):
+        _clean(iterative)
+        self.s = 0.5 * boltzmann * self.temp * np.random.normal(size=(self.ns, iterative.pos.size))
+        evals, evecs = np.linalg.eig(-self.a_p * iterative.timestep / 2)
+        self.t = np.dot(evecs * np.exp(evals), np.linalg.inv(evecs)).real
+        self.S = stabilized_cholesky_decomp(self.c_p - self.t @ self.c_p @ self.t.T).real
+        self.n_atoms = iterative.pos.shape[0]
+
+    def thermo(self, iterative):
+        before = iterative.ekin
+        root_m = np.sqrt(iterative.masses).reshape(-1, 1)
+        old = np.vstack([(root_m * iterative.vel).reshape(-1), self.s])
+        new = self.t @ old + self.S @ np.random.normal(size=(self.ns + 1, 3 * self.n_atoms))
+        iterative.vel[:] = new[0].reshape(self.n_atoms, 3) / root_m
+        self.s[:] = new[1:]
+        iterative.ekin = iterative._compute_ekin()
+        self.econs_correction += before - iterative.ekin
+
+    def pre(self, iterative, G1_add=None):
+        self.thermo(iterative)
+
+    def post(self, iterative, G1_add=None):
+        self.thermo(iterative)
 
 
 class NHChain(object):

@@ -7,7 +7,7 @@ from ..units import boltzmann
 
 __all__ = [
     "get_random_vel", "remove_com_moment", "clean_momenta", "get_ndof_internal_md", "domain_symmetrize",
-    "get_random_vel_press", "get_ndof_baro",
+    "get_random_vel_press", "get_ndof_baro", "stabilized_cholesky_decomp",
 ]
 
 
@@ -83,3 +83,18 @@ def get_ndof_baro(dim, anisotropic, vol_constraint):
     if ndof == 0:
         raise AssertionError("Isotropic barostat called with a volume constraint.")
     return ndof
+
+
+def stabilized_cholesky_decomp(mat):
+    """Factor M with M M^T = mat for a symmetric matrix that may be slightly indefinite: plain Cholesky when positive
+    definite, else L D L^T with the negative pivots of D clipped to zero (sampling/utils.py:504-528)."""
+    if np.all(np.linalg.eigvals(mat) > 0):
+        return np.linalg.cholesky(mat)
+    n = mat.shape[0]
+    diag, low = np.zeros(n), np.eye(n)
+    for i in range(n):
+        for j in range(i):
+            acc = mat[i, j] - np.sum(low[i, :j] * low[j, :j] * diag[:j])
+            low[i, j] = acc / diag[j] if abs(diag[j]) > 1e-12 else 0.0
+        diag[i] = mat[i, i] - np.sum(low[i, :i] ** 2 * diag[:i])
+    return low * np.sqrt(diag.clip(min=0))
