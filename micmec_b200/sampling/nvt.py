@@ -46,7 +46,6 @@ class AndersenThermostat(VerletHook):
         self.select = select
         self.annealing = annealing
         VerletHook.__init__(self, start, step)
-        self.start, self.step = start, step  # kept for callers that inspect them; Verlet hooks fire every step
 
     def init(self, iterative):
         _clean(iterative)
@@ -125,8 +124,6 @@ class LangevinThermostat(VerletHook):
     def post(self, iterative, G1_add=None):
         self._half_step(iterative)
 
-    thermo = _half_step
-
 
 class CSVRThermostat(VerletHook):
     """Canonical sampling through stochastic velocity rescaling (nvt.py:221-274)."""
@@ -189,7 +186,7 @@ class GLEThermostat(VerletHook):
         root_m = np.sqrt(iterative.masses).reshape(-1, 1)
         old = np.vstack([(root_m * iterative.vel).reshape(-1), self.s])
         new = self.t @ old + self.S @ np.random.normal(size=(self.ns + 1, 3 * self.n_atoms))
-        iterative.vel[:] = new[0].reshape(self.n_atoms, 3) / root_m
+        iterative.vel[:] = np.sqrt(1.0 / iterative.masses).reshape(-1, 1) * new[0].reshape(self.n_atoms, 3)
         self.s[:] = new[1:]
         iterative.ekin = iterative._compute_ekin()
         self.econs_correction += before - iterative.ekin

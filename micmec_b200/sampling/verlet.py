@@ -172,6 +172,8 @@ class VerletIntegrator(Iterative):
         if len(vhooks) > 1:
             return None
         for hook in vhooks:
+            if not hook.native:  # Langevin / Berendsen / ... hooks, an MTK barostat with its own chain, user hooks
+                return None
             if isinstance(hook, TBCombination):
                 thermo, baro = hook.thermostat, hook.barostat
             elif isinstance(hook, NHCThermostat):

@@ -53,6 +53,33 @@ class Domain(object):
         out.setflags(write=False)
         return out
 
+    def _full(self, reciprocal):
+        """3x3 completion of the cell (ext.pyx:56-72): identity for nvec = 0, the cell itself for nvec = 3, else the
+        periodic vectors followed by an orthonormal complement (reciprocal: the matching dual basis)."""
+        nvec = self.nvec
+        if nvec == 3:
+            return (self._gvecs if reciprocal else self._rvecs).copy()
+        if nvec == 0:
+            return np.identity(3)
+        up, sp, vt = np.linalg.svd(self._rvecs, full_matrices=True)
+        sing, u = np.ones(3), np.identity(3)
+        sing[:nvec], u[:nvec, :nvec] = sp, up
+        if reciprocal:
+            return np.dot(u / sing, vt)
+        full = np.dot(u * sing, vt)
+        full[:nvec] = self._rvecs
+        return full
+
+    def _get_rvecs(self, full=False):
+        out = self._full(False) if full else self._rvecs.copy()
+        out.setflags(write=False)
+        return out
+
+    def _get_gvecs(self, full=False):
+        out = self._full(True) if full else self._gvecs.copy()
+        out.setflags(write=False)
+        return out
+
     @property
     def parameters(self):
         """Lengths and angles (ext.pyx:108-121)."""

@@ -16,6 +16,12 @@ Contents
   multistate.npz            synthetic 2- and 3-state types injected into 3x3x3_test / 3x3x3_conf0
   traj_<ensemble>.npz       100-step NVE / NVT(NHC) / NPT(NHC+MTK, aniso + iso) / NPH(MTK) trajectories of the
                             reference VerletIntegrator with recorded initial vel0 / chain / barostat state
+  hooks_<case>.npz          30-step trajectories with the reference's other Verlet hooks (Langevin / Berendsen /
+                            CSVR / Andersen / GLE thermostats, Langevin / Berendsen barostats, MTK with its own chain),
+                            global NumPy RNG seeded with 42 right before the integrator is constructed: a replacement
+                            that consumes the RNG in the same order reproduces them
+  opt_<case>.npz            QNOptimizer runs (CartesianDOF, StrainCellDOF free / frozen, FullCellDOF): x, f, g, trust
+                            radius and convergence bookkeeping after every iteration
 """
 import os
 import sys
@@ -34,8 +40,10 @@ from micmec.pes.mmff import MicMecForceField, ForcePartMechanical  # noqa: E402
 from micmec.pes import nanocell, nanocell_original, nanocell_utils  # noqa: E402
 from micmec.sampling.verlet import VerletIntegrator, VerletHook  # noqa: E402
 from micmec.sampling.iterative import Hook  # noqa: E402
-from micmec.sampling.nvt import NHCThermostat  # noqa: E402
-from micmec.sampling.npt import MTKBarostat, TBCombination  # noqa: E402
+from micmec.sampling.nvt import (  # noqa: E402
+    NHCThermostat, AndersenThermostat, BerendsenThermostat, LangevinThermostat, CSVRThermostat, GLEThermostat,
+)
+from micmec.sampling.npt import MTKBarostat, TBCombination, BerendsenBarostat, LangevinBarostat  # noqa: E402
 from molmod.units import femtosecond, pascal  # noqa: E402
 
 DATA = os.path.join(refenv.REFERENCE, "data")
@@ -257,7 +265,112 @@ def make_traj(tag, name, ensemble, model="original", nsteps=100, amp=0.3, **opts
     refenv.use_model("original")
 
 
+HOOK_CASES = {
+    # tag: (fixture, builder(mmf, timestep) -> list of Verlet hooks); time constants as in simulations/md.py:57-66
+    # unless the class default is unstable for these stiff cells (see the note in make_traj)
+    "nvt_langevin": ("3x3x3_test", lambda mmf, dt: [LangevinThermostat(300.0, timecon=100 * dt)]),
+    "npt_langevin": ("3x3x3_conf0", lambda mmf, dt: [TBCombination(
+        LangevinThermostat(300.0, timecon=100 * dt), LangevinBarostat(mmf, 300.0, 1e6 * pascal, timecon=1e4 * dt))]),
+    "npt_langevin_iso": ("2x2x2_fcu", lambda mmf, dt: [TBCombination(
+        LangevinThermostat(300.0, timecon=100 * dt),
+        LangevinBarostat(mmf, 300.0, 1e6 * pascal, timecon=1e4 * dt, anisotropic=False))]),
+    "npt_berendsen": ("3x3x3_test", lambda mmf, dt: [TBCombination(
+        BerendsenThermostat(300.0, timecon=100 * femtosecond),
+        BerendsenBarostat(mmf, 300.0, 1e6 * pascal, timecon=1e5 * femtosecond))]),
+    "nvt_berendsen": ("5x5x5_fcu_hollow", lambda mmf, dt: [BerendsenThermostat(250.0, timecon=200 * femtosecond)]),
+    "nvt_csvr": ("3x3x3_conf3", lambda mmf, dt: [CSVRThermostat(300.0, timecon=100 * femtosecond)]),
+    "nvt_andersen": ("2x2x2_test", lambda mmf, dt: [AndersenThermostat(300.0, annealing=0.99)]),
+    "nvt_gle": ("2x2x2_reo", lambda mmf, dt: [GLEThermostat(300.0, np.array([[2e-3, 1e-3], [-1e-3, 4e-3]]))]),
+    "npt_langevin_mtk": ("3x3x3_conf9", lambda mmf, dt: [TBCombination(
+        LangevinThermostat(300.0, timecon=100 * dt), MTKBarostat(mmf, 300.0, 1e6 * pascal, timecon=1e5 * femtosecond))]),
+    "nph_mtk_own_chain": ("3x3x3_test", lambda mmf, dt: [MTKBarostat(
+        mmf, 300.0, 1e6 * pascal, timecon=1e5 * femtosecond, baro_thermo=NHCThermostat(300.0, timecon=100 * femtosecond))]),
+}
+
+
+def make_hook_traj(tag, nsteps=30, amp=0.3):
+    name, builder = HOOK_CASES[tag]
+    refenv.use_model("original")
+    system = load(name)
+    system.pos[:] = system.pos + amp * np.random.default_rng(5).standard_normal(system.pos.shape)
+    out = system_arrays(system)  # geometry BEFORE any hook symmetrises the domain: the replacement starts from here
+    fpm = ForcePartMechanical(system)
+    mmf = MicMecForceField(system, [fpm])
+    timestep = 10.0 * femtosecond
+    np.random.seed(42)
+    hooks = builder(mmf, timestep)
+    counters = [0, 1, 2, 10, nsteps]
+    hooks.append(Recorder(counters, out))
+    verlet = VerletIntegrator(mmf, timestep=timestep, hooks=hooks, temp0=300.0)
+    verlet.run(nsteps)
+    for counter in counters:
+        assert np.isfinite(out["step%d:epot" % counter]) and out["step%d:temp" % counter] < 3000.0, (tag, counter)
+    out["meta:timestep"], out["meta:ndof"], out["meta:nsteps"] = timestep, float(verlet.ndof), nsteps
+    out["meta:counters"] = np.array(counters)
+    np.savez_compressed(os.path.join(HERE, "hooks_%s.npz" % tag), **out)
+
+
+class OptRecorder(Hook):
+    def __init__(self, store):
+        Hook.__init__(self, 0, 1)
+        self.store = store
+
+    def __call__(self, it):
+        p = "iter%d:" % it.counter
+        self.store[p + "x"], self.store[p + "f"], self.store[p + "g"] = it.x.copy(), float(it.f), it.g.copy()
+        self.store[p + "trust_radius"] = float(it.trust_radius)
+        self.store[p + "conv_val"], self.store[p + "conv_count"] = float(it.dof.conv_val), int(it.dof.conv_count)
+        self.store[p + "pos"] = it.mmf.system.pos.copy()
+        self.store[p + "rvecs"] = np.array(it.mmf.system.domain.rvecs)
+
+
+OPT_CASES = {
+    # tag: (fixture, dof kind, dof kwargs, perturbation amplitude, cell strain, max iterations)
+    "cartesian_3x3x3_conf0": ("3x3x3_conf0", "cartesian", dict(gpos_rms=1e-7, dpos_rms=1e-5), 0.5, None, 60),
+    "cartesian_5x5x5_fcu_hollow": ("5x5x5_fcu_hollow", "cartesian", dict(), 0.4, None, 60),
+    "strain_3x3x3_test": ("3x3x3_test", "strain",
+                          dict(gpos_rms=1e-8, dpos_rms=1e-6, grvecs_rms=1e-8, drvecs_rms=1e-6), 0.3,
+                          np.array([[1.02, 0.01, 0.0], [0.01, 0.98, -0.015], [0.0, -0.015, 1.01]]), 80),
+    "strain_frozen_3x3x3_conf3": ("3x3x3_conf3", "strain", dict(do_frozen=True), 0.0,
+                                  np.array([[0.97, 0.0, 0.02], [0.0, 1.03, 0.0], [0.02, 0.0, 1.0]]), 40),
+    "fullcell_2x2x2_reo": ("2x2x2_reo", "full", dict(), 0.2,
+                           np.array([[1.01, 0.0, 0.0], [0.0, 0.99, 0.01], [0.0, 0.01, 1.0]]), 60),
+}
+
+
+def make_opt(tag):
+    from micmec.sampling.opt import QNOptimizer
+    from micmec.sampling.dof import CartesianDOF, StrainCellDOF, FullCellDOF
+
+    name, kind, kwargs, amp, strain, maxiter = OPT_CASES[tag]
+    refenv.use_model("original")
+    system = load(name)
+    if strain is not None:
+        system.domain.update_rvecs(np.ascontiguousarray(np.dot(np.array(system.domain.rvecs), strain)))
+        system.pos[:] = np.dot(system.pos, strain)
+    system.pos[:] = system.pos + amp * np.random.default_rng(9).standard_normal(system.pos.shape)
+    out = system_arrays(system)
+    mmf = MicMecForceField(system, [ForcePartMechanical(system)])
+    dof = {"cartesian": CartesianDOF, "strain": StrainCellDOF, "full": FullCellDOF}[kind](mmf, **kwargs)
+    opt = QNOptimizer(dof, hooks=[OptRecorder(out)])
+    opt.run(maxiter)
+    out["meta:iterations"], out["meta:converged"] = opt.counter, int(dof.converged)
+    out["meta:kind"] = np.array(kind)
+    for key, val in kwargs.items():
+        out["kw:" + key] = val
+    np.savez_compressed(os.path.join(HERE, "opt_%s.npz" % tag), **out)
+    print(tag, "iterations", opt.counter, "converged", dof.converged, "f", opt.f)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "opt":
+        for tag in OPT_CASES:
+            make_opt(tag)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "hooks":
+        for tag in HOOK_CASES:
+            make_hook_traj(tag)
+        return
     make_cells()
     for name in FIXTURES:
         make_force(name)
@@ -269,6 +382,10 @@ def main():
     make_traj("npt_iso_3x3x3_test", "3x3x3_test", "npt", anisotropic=False)
     make_traj("npt_volc_2x2x2_reo", "2x2x2_reo", "npt", vol_constraint=True)
     make_traj("nph_3x3x3_conf3", "3x3x3_conf3", "nph")
+    for tag in HOOK_CASES:
+        make_hook_traj(tag)
+    for tag in OPT_CASES:
+        make_opt(tag)
     print("golden vectors written to", HERE)
 
 
