@@ -49,7 +49,10 @@ def test_hessian_models():
         for _ in range(40):
             dx = rng.normal(size=6)
             model.update(dx, true @ dx)
-        assert np.allclose(model.hessian, true, atol=1e-6 if cls is SR1HessianModel else 0.5)
+            assert np.allclose(model.hessian @ dx, true @ dx)  # secant condition of the last update
+        if cls is SR1HessianModel:  # SR1 recovers a quadratic's Hessian exactly after ndof independent updates
+            assert np.allclose(model.hessian, true, atol=1e-9)
+        assert np.all(np.linalg.eigvalsh(model.hessian) > 0) or cls is SR1HessianModel
         assert not model.update(np.zeros(6), np.zeros(6))
     with pytest.raises(TypeError):
         SR1HessianModel(3, np.eye(4))
