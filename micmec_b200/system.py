@@ -150,6 +150,15 @@ class System(object):
         output.update(self.params)
         dump_chk(fn, {k: v for k, v in output.items() if v is not None})
 
+    def to_hdf5(self, f):
+        """Write ``system/pos`` and ``system/masses`` into an open, writable h5py file (system.py:352-370)."""
+        if "system" in f:
+            raise ValueError("The HDF5 file already contains a system description.")
+        sgrp = f.create_group("system")
+        sgrp.create_dataset("pos", data=self.pos)
+        if self.masses is not None:
+            sgrp.create_dataset("masses", data=self.masses)
+
     @classmethod
     def periodic_grid(cls, shape, type_params, explicit=None):
         """Full periodic ``nx x ny x nz`` grid of ONE cell type at rest, in closed form.

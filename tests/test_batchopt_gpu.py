@@ -36,3 +36,17 @@ def test_replica_optimiser_on_gpu_matches_oracle_driven_run(kind):
         assert np.max(np.abs(gpu.rvecs[r] - cpu.rvecs[r])) <= 1e-6 * np.sqrt(np.mean(cpu.rvecs[r] ** 2)), r
         assert abs(gpu.f[r] - cpu.f[r]) <= 1e-8 * float(cpu.f_old.max()) + 1e-12, r
         assert abs(int(gpu.iterations[r]) - int(cpu.iterations[r])) <= 6, r
+
+
+def test_batched_eigh_on_gpu_reconstructs_the_models():
+    """Batches of 64 or more Hessian models are diagonalised on the GPU (cuSOLVER through torch)."""
+    from micmec_b200.sampling.batchopt import _eigh
+
+    rng = np.random.default_rng(2)
+    a = rng.normal(size=(96, 87, 87))
+    h = a + a.transpose(0, 2, 1)
+    evals, evecs = _eigh(h)
+    assert evals.shape == (96, 87) and np.all(np.diff(evals, axis=1) >= 0)
+    back = np.einsum("rij,rj,rkj->rik", evecs, evals, evecs)
+    assert np.max(np.abs(back - h)) <= 1e-10 * np.max(np.abs(h))
+    assert np.allclose(evals, np.linalg.eigvalsh(h), rtol=0, atol=1e-10 * np.max(np.abs(h)))
