@@ -538,6 +538,7 @@ static void fill_args(mm_handle *h, MarchArgs &a) {
     a.minv = g.minv;
     a.type = g.type;
     a.sc = g.d_sc;
+    a.spg = g.d_sp;
     a.partials = g.d_partials;
     a.fused = 0;
     a.wrap_lo = a.wrap_hi = 0.0;

@@ -112,6 +112,7 @@ struct MarchArgs {
     double wrap_lo, wrap_hi;
     int fused;
     const StepConsts *sc;
+    const SParams *spg;  // the constants once more in global memory (pinned register copies are loaded from here)
     double *partials;
 };
 
