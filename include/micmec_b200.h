@@ -122,6 +122,15 @@ int mm_profile(mm_handle *h, int64_t nlaunch[2], double total_ms[2]);
 int mm_set_rvecs_batch(mm_handle *h, const double *rvecs_host /* [nreplicas][3][3] */);
 int mm_get_replica_results(mm_handle *h, double *energies_host /* [nreplicas] */, double *vtens_host /* [nreplicas][3][3] or NULL */);
 
+/* ---- batched dense symmetric eigen-decomposition --------------------------------------------------------------- */
+/* numpy.linalg.eigh as QNOptimizer uses it on its Hessian model (micmec/sampling/opt.py:196-197 get_spectrum, called at
+ * :334-336), for `batch` independent n x n matrices at once (1 <= n <= 96; one thread block per matrix, two-sided cyclic
+ * Jacobi in shared memory).  mats [batch][n][n] row-major (symmetrised on load); evals [batch][n] ascending; evecs
+ * [batch][n][n] with eigenvector i in COLUMN i, as numpy returns them.  `where` applies to all three arrays.
+ * max_sweeps_out (may be NULL) receives the largest number of Jacobi sweeps any matrix needed (30 = not converged). */
+int mm_batched_eigh(int device, int64_t batch, int32_t n, const double *mats, int where, double *evals, double *evecs,
+                    int32_t *max_sweeps_out);
+
 /* ---- multi-GPU (no reference counterpart: the reference is single-process) ---------------------------------- */
 /* NCCL bootstrap: rank 0 creates a 128-byte unique id, the host side broadcasts it (torch.distributed), every rank
  * calls mm_comm_init.  nccl_path: the libnccl.so.2 to dlopen (NULL: the one already loaded in the process).

@@ -28,18 +28,32 @@ def _norm(a):
     return np.sqrt((a * a).sum(axis=-1))
 
 
-def _eigh(h):
-    """Batched symmetric eigen-decomposition [R, n, n].  cuSOLVER through torch when a GPU is present (the batch of
-    10240 87x87 models of config 5 is LAPACK-bound on the host otherwise), NumPy/LAPACK when not."""
-    try:
-        import torch
+def _eigh(h, device=0, backend="device"):
+    """Batched symmetric eigen-decomposition [R, n, n] -> (evals [R, n] ascending, evecs [R, n, n], columns).
 
-        if torch.cuda.is_available() and h.shape[0] >= 64:
-            evals, evecs = torch.linalg.eigh(torch.from_numpy(h).cuda())
-            return evals.cpu().numpy(), evecs.cpu().numpy()
-    except ImportError:  # pragma: no cover
-        pass
-    return np.linalg.eigh(h)
+    ``backend="device"`` (the product path): ``mm_batched_eigh`` on the B200 - one thread block per matrix, cyclic Jacobi
+    in shared memory.  The 10 240 81 x 81 Hessian models of config 5 per sweep are LAPACK-bound on the host (~0.7 ms
+    each) and ``torch.linalg.eigh`` loops cuSOLVER's syevd over the batch for n > 32, which is no faster.  It fails
+    loudly without a usable device.  ``backend="lapack"`` must be asked for explicitly; the CPU tests of the host logic
+    do."""
+    if backend == "lapack":
+        return np.linalg.eigh(h)
+    if backend != "device":
+        raise ValueError("eigh backend must be 'device' or 'lapack'")
+    import ctypes
+
+    from .. import _lib
+
+    lib = _lib.load()
+    h = np.ascontiguousarray(h, dtype=float)
+    evals = np.empty(h.shape[:2])
+    evecs = np.empty(h.shape)
+    worst = ctypes.c_int32()
+    _lib.check(lib.mm_batched_eigh(int(device), h.shape[0], h.shape[1], _lib.ptr(h), _lib.MM_HOST, _lib.ptr(evals),
+                                   _lib.ptr(evecs), ctypes.byref(worst)))
+    if worst.value >= 30:
+        raise RuntimeError("mm_batched_eigh: a Hessian model did not converge in 30 Jacobi sweeps")
+    return evals, evecs
 
 
 def solve_trust_radius_batch(grad, evals, radius, threshold=1e-5, maxiter=20000):
@@ -115,6 +129,8 @@ class ReplicaQNOptimizer(object):
     gpos_rms, dpos_rms, grvecs_rms, drvecs_rms : convergence thresholds with the meaning (and the automatic 3x max
         thresholds) of dof.py:133-193, 382-449.
     trust_radius, small_radius, too_small_radius : as ``QNOptimizer`` (opt.py:262-300).
+    device : CUDA device ordinal for the batched eigen-decompositions (the one ``batch`` lives on).
+    eigh : "device" (``mm_batched_eigh``; fails without a GPU) or "lapack" (host; only for tests of the host logic).
 
     Attributes after / during ``run``: ``x``, ``f``, ``g`` (current accepted point), ``pos``, ``rvecs``, ``converged``,
     ``failed`` (trust radius underflow: the reference raises RuntimeError there), ``iterations`` (accepted steps per
@@ -122,10 +138,12 @@ class ReplicaQNOptimizer(object):
     """
 
     def __init__(self, batch, pos0, rvecs0, dof="cartesian", gpos_rms=1e-5, dpos_rms=1e-3, grvecs_rms=1e-5,
-                 drvecs_rms=1e-3, trust_radius=1.0, small_radius=1e-5, too_small_radius=1e-10):
+                 drvecs_rms=1e-3, trust_radius=1.0, small_radius=1e-5, too_small_radius=1e-10, device=0, eigh="device"):
         if dof not in ("cartesian", "strain"):
             raise ValueError("dof must be 'cartesian' or 'strain'")
         self.batch = batch
+        self.device = device
+        self.eigh_backend = eigh
         self.kind = dof
         pos0 = np.array(pos0, dtype=float)
         self.rvecs0 = np.array(rvecs0, dtype=float)
@@ -174,6 +192,7 @@ class ReplicaQNOptimizer(object):
         self._evecs = np.zeros((n, self.ndof, self.ndof))
         self._grad_eigen = np.zeros((n, self.ndof))
         self._started = np.zeros(n, bool)    # first check_convergence call done
+        self._rank1 = None                   # scratch for the rank-one terms of the SR1 update
 
     # ---- DOF mappings ----------------------------------------------------------------------------------------------
     @staticmethod
@@ -245,24 +264,39 @@ class ReplicaQNOptimizer(object):
 
     # ---- the state machine of QNOptimizer.propagate / make_step (opt.py:322-393) ---------------------------------------
     def _refresh_models(self):
-        """SR1 update and new spectrum for the replicas that accepted a step last sweep."""
-        upd = np.flatnonzero(self._fresh & (self.iterations > 0))
-        if upd.size:
-            dx, dg = self.x[upd] - self.x_old[upd], self.g[upd] - self.g_old[upd]
-            resid = dg - np.einsum("rij,rj->ri", self.hessian[upd], dx)
+        """SR1 update and new spectrum for the replicas that accepted a step last sweep.  Written to touch the
+        [R, ndof, ndof] arrays as few times as possible (they are 0.5 GB each for config 5): the rank-one term is
+        formed for all replicas with a zero coefficient where no update applies, and subsets are only gathered when
+        they are proper subsets."""
+        upd_mask = self._fresh & (self.iterations > 0)
+        if upd_mask.any():
+            dx = np.where(upd_mask[:, None], self.x - self.x_old, 0.0)
+            dg = np.where(upd_mask[:, None], self.g - self.g_old, 0.0)
+            resid = dg - np.einsum("rij,rj->ri", self.hessian, dx)
             denom = (resid * dx).sum(axis=1)
-            safe = abs(denom) > 1e-5 * _norm(dx) * _norm(resid)
-            ok, bad = upd[safe], upd[~safe]
+            safe = upd_mask & (abs(denom) > 1e-5 * _norm(dx) * _norm(resid))
             with np.errstate(divide="ignore", invalid="ignore"):
-                self.hessian[ok] += resid[safe][:, :, None] * resid[safe][:, None, :] / denom[safe][:, None, None]
-            self.hessian[bad] = np.identity(self.ndof)
-            self.trust_radius[bad] = self.initial_trust_radius
+                coef = np.where(safe, 1.0 / np.where(safe, denom, 1.0), 0.0)
+            if self._rank1 is None:
+                self._rank1 = np.empty_like(self.hessian)
+            np.multiply(resid[:, :, None], (coef[:, None] * resid)[:, None, :], out=self._rank1)
+            self.hessian += self._rank1
+            bad = np.flatnonzero(upd_mask & ~safe)
+            if bad.size:  # a failed update poisons the model: identity and the initial radius again (opt.py:325-329)
+                self.hessian[bad] = np.identity(self.ndof)
+                self.trust_radius[bad] = self.initial_trust_radius
+            upd = np.flatnonzero(upd_mask)
             self.x_old[upd], self.f_old[upd], self.g_old[upd] = self.x[upd], self.f[upd], self.g[upd]
-        new = np.flatnonzero(self._fresh & ~(self.converged | self.failed))
-        if new.size:
-            self._evals[new], self._evecs[new] = _eigh(self.hessian[new])
-            self._grad_eigen[new] = np.einsum("rji,rj->ri", self._evecs[new], self.g_old[new])
-            self._fresh[new] = False
+        new_mask = self._fresh & ~(self.converged | self.failed)
+        if new_mask.all():
+            self._evals, self._evecs = _eigh(self.hessian, self.device, self.eigh_backend)
+            self._grad_eigen = np.einsum("rji,rj->ri", self._evecs, self.g_old)
+        elif new_mask.any():
+            new = np.flatnonzero(new_mask)
+            evals, evecs = _eigh(self.hessian[new], self.device, self.eigh_backend)
+            self._evals[new], self._evecs[new] = evals, evecs
+            self._grad_eigen[new] = np.einsum("rji,rj->ri", evecs, self.g_old[new])
+        self._fresh[new_mask] = False
 
     def sweep(self):
         """One batched force evaluation: every live replica tries a step and either accepts it or shrinks its radius."""

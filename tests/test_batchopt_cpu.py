@@ -68,7 +68,7 @@ def test_replica_optimiser_matches_single_system_runs(kind):
         systems = replicas(["3x3x3_test", "3x3x3_conf0"], 2, 0.3, strain=0.02)
     pos0 = np.stack([s.pos for s in systems])
     rvecs0 = np.stack([np.array(s.domain.rvecs) for s in systems])
-    opt = ReplicaQNOptimizer(OracleReplicaEvaluator(systems), pos0, rvecs0, dof=kind, **kwargs)
+    opt = ReplicaQNOptimizer(OracleReplicaEvaluator(systems), pos0, rvecs0, dof=kind, eigh="lapack", **kwargs)
     sweeps = opt.run(300)
     assert opt.converged.all() and not opt.failed.any()
     assert opt.evaluations == sweeps + 1  # one batched force call per sweep

@@ -27,7 +27,7 @@ def test_replica_optimiser_on_gpu_matches_oracle_driven_run(kind):
     sweeps = gpu.run(400)
     assert gpu.converged.all() and not gpu.failed.any()
     assert gpu.evaluations == sweeps + 1 and batch.launches > 0
-    cpu = ReplicaQNOptimizer(OracleReplicaEvaluator(replicas(*args)), pos0, rvecs0, dof=kind, **kwargs)
+    cpu = ReplicaQNOptimizer(OracleReplicaEvaluator(replicas(*args)), pos0, rvecs0, dof=kind, eigh="lapack", **kwargs)
     cpu.run(400)
     assert cpu.converged.all()
     for r in range(len(systems)):
@@ -38,15 +38,32 @@ def test_replica_optimiser_on_gpu_matches_oracle_driven_run(kind):
         assert abs(int(gpu.iterations[r]) - int(cpu.iterations[r])) <= 6, r
 
 
-def test_batched_eigh_on_gpu_reconstructs_the_models():
-    """Batches of 64 or more Hessian models are diagonalised on the GPU (cuSOLVER through torch)."""
+@pytest.mark.parametrize("n", [1, 2, 27, 81, 87, 96])
+def test_batched_eigh_on_gpu_matches_lapack(n):
+    """mm_batched_eigh (cyclic Jacobi, one block per matrix) against numpy.linalg.eigh: eigenvalues, reconstruction,
+    orthogonality, ascending order - random matrices, the identity, SR1-like low-rank updates of it."""
     from micmec_b200.sampling.batchopt import _eigh
 
     rng = np.random.default_rng(2)
-    a = rng.normal(size=(96, 87, 87))
+    a = rng.normal(size=(150, n, n))
     h = a + a.transpose(0, 2, 1)
-    evals, evecs = _eigh(h)
-    assert evals.shape == (96, 87) and np.all(np.diff(evals, axis=1) >= 0)
+    h[0] = np.eye(n)
+    u = rng.normal(size=(n,))
+    h[1] = np.eye(n) + 0.37 * np.outer(u, u)
+    h[2] = 0.0
+    h[3] *= 1e-12
+    evals, evecs = _eigh(h, 0, "device")
+    scale = np.max(np.abs(h), axis=(1, 2)) + 1e-300
+    assert evals.shape == (150, n) and np.all(np.diff(evals, axis=1) >= 0)
     back = np.einsum("rij,rj,rkj->rik", evecs, evals, evecs)
-    assert np.max(np.abs(back - h)) <= 1e-10 * np.max(np.abs(h))
-    assert np.allclose(evals, np.linalg.eigvalsh(h), rtol=0, atol=1e-10 * np.max(np.abs(h)))
+    assert np.max(np.max(np.abs(back - h), axis=(1, 2)) / scale) <= 1e-13 * n
+    gram = np.einsum("rki,rkj->rij", evecs, evecs)
+    assert np.max(np.abs(gram - np.eye(n))) <= 1e-13 * n
+    assert np.max(np.max(np.abs(evals - np.linalg.eigvalsh(h)), axis=1) / scale) <= 1e-13 * n
+
+
+def test_batched_eigh_rejects_bad_sizes():
+    from micmec_b200.sampling.batchopt import _eigh
+
+    with pytest.raises(ValueError):
+        _eigh(np.zeros((2, 97, 97)), 0, "device")
