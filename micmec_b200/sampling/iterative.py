@@ -1,9 +1,12 @@
-"""Iterative algorithm scaffolding: hooks and state items (same protocol as micmec/sampling/iterative.py).
+"""Scaffolding of the iterative algorithms (integrator, optimisers): hooks and state items.
 
-Hooks written for the reference keep working: a hook is any object with ``expects_call(counter)`` and
-``__call__(iterative)``; a state item exposes ``key``, ``update(iterative)``, ``value``, ``shape``, ``dtype``,
-``iter_attrs``.  The run loop itself lives in the subclass because the device integrator advances many steps per
-launch sequence instead of one ``propagate`` per Python iteration.
+The PROTOCOL is the one of micmec/sampling/iterative.py:41-222, so that hooks and state items written for the reference
+keep working: a hook is any object with ``expects_call(counter)`` and ``__call__(iterative)``; a state item has ``key``,
+``update(iterative)``, ``value``, ``shape``, ``dtype``, ``iter_attrs(iterative)`` and ``copy()``; an ``Iterative`` exposes
+``state_list`` / ``state``, ``hooks``, ``counter``, ``initialize``, ``call_hooks``, ``run``, ``propagate``, ``finalize``.
+The implementation is this package's own: state items are declared by a getter function instead of one hand-written class
+each, and the state snapshot is refreshed lazily - only at iterations where some hook actually fires, which matters for
+the device-resident integrator (a refresh of ``pos`` / ``vel`` is a device-to-host copy).
 """
 import numpy as np
 
@@ -14,130 +17,111 @@ __all__ = [
 
 
 class Hook(object):
-    """Something called every ``step`` iterations from iteration ``start`` on (iterative.py:198-222)."""
+    """Called at iterations ``start, start + step, start + 2 step, ...``."""
 
-    name = None
-    kind = None
-    method = None
+    name = kind = method = None
 
     def __init__(self, start=0, step=1):
-        self.start = start
-        self.step = step
+        self.start, self.step = start, step
 
     def expects_call(self, counter):
-        return counter >= self.start and (counter - self.start) % self.step == 0
+        since = counter - self.start
+        return since >= 0 and since % self.step == 0
 
     def __call__(self, iterative):
         raise NotImplementedError
 
 
 class StateItem(object):
-    def __init__(self, key):
+    """One named quantity of the running algorithm.  ``update`` stores the current ``value``; ``shape`` and ``dtype``
+    are fixed by the first update (trajectory writers size their datasets from them).  Subclasses either override
+    ``get_value`` (the reference's way) or pass ``getter`` / ``attrs`` callables."""
+
+    def __init__(self, key, getter=None, attrs=None):
         self.key = key
-        self.shape = None
-        self.dtype = None
+        self.shape = self.dtype = None
+        self._getter, self._attrs = getter, attrs
+
+    def get_value(self, iterative):
+        if self._getter is None:
+            raise NotImplementedError
+        return self._getter(iterative)
 
     def update(self, iterative):
-        self.value = self.get_value(iterative)
-        if self.shape is None:
-            if isinstance(self.value, np.ndarray):
-                self.shape, self.dtype = self.value.shape, self.value.dtype
-            else:
-                self.shape, self.dtype = tuple([]), type(self.value)
-
-    def get_value(self, iterative):
-        raise NotImplementedError
+        value = self.value = self.get_value(iterative)
+        if self.shape is not None:
+            return
+        if isinstance(value, np.ndarray):
+            self.shape, self.dtype = value.shape, value.dtype
+        else:
+            self.shape, self.dtype = (), type(value)
 
     def iter_attrs(self, iterative):
-        return []
+        return [] if self._attrs is None else list(self._attrs(iterative))
 
     def copy(self):
-        return self.__class__()
+        return type(self)()
 
 
-class AttributeStateItem(StateItem):
-    def get_value(self, iterative):
-        return getattr(iterative, self.key, None)
-
-    def copy(self):
-        return self.__class__(self.key)
-
-
-class PosStateItem(StateItem):
-    def __init__(self):
-        StateItem.__init__(self, "pos")
-
-    def get_value(self, iterative):
-        return iterative.mmf.system.pos
-
-
-class TemperatureStateItem(StateItem):
-    def __init__(self):
-        StateItem.__init__(self, "temp")
-
-    def get_value(self, iterative):
-        return getattr(iterative, "temp", None)
-
-    def iter_attrs(self, iterative):
-        yield "ndof", iterative.ndof
-
-
-class VolumeStateItem(StateItem):
-    def __init__(self):
-        StateItem.__init__(self, "volume")
-
-    def get_value(self, iterative):
-        return iterative.mmf.system.domain.volume
-
-
-class DomainStateItem(StateItem):
-    def __init__(self):
-        StateItem.__init__(self, "domain")
-
-    def get_value(self, iterative):
-        return iterative.mmf.system.domain.rvecs
-
-
-class ConsErrStateItem(StateItem):
-    def get_value(self, iterative):
-        return getattr(iterative._cons_err_tracker, self.key, None)
+class _KeyedItem(StateItem):
+    """State item whose constructor takes the key (``AttributeStateItem("epot")``)."""
 
     def copy(self):
-        return self.__class__(self.key)
+        return type(self)(self.key)
 
 
-class EPotContribStateItem(StateItem):
+class AttributeStateItem(_KeyedItem):
+    """``getattr(iterative, key)`` (``None`` while the attribute does not exist yet)."""
+
+    def __init__(self, key):
+        StateItem.__init__(self, key, getter=lambda it: getattr(it, key, None))
+
+
+class ConsErrStateItem(_KeyedItem):
+    """An attribute of the integrator's conserved-quantity tracker."""
+
+    def __init__(self, key):
+        StateItem.__init__(self, key, getter=lambda it: getattr(it._cons_err_tracker, key, None))
+
+
+def _fixed_item(name, key, getter, attrs=None, doc=""):
+    """Class of a state item with a fixed key: ``PosStateItem()`` and friends."""
+
     def __init__(self):
-        StateItem.__init__(self, "epot_contribs")
+        StateItem.__init__(self, key, getter=getter, attrs=attrs)
 
-    def get_value(self, iterative):
-        return np.array([part.energy for part in iterative.mmf.parts])
+    return type(name, (StateItem,), {"__init__": __init__, "__doc__": doc})
 
-    def iter_attrs(self, iterative):
-        yield "epot_contrib_names", np.array([part.name for part in iterative.mmf.parts], dtype="S")
+
+PosStateItem = _fixed_item("PosStateItem", "pos", lambda it: it.mmf.system.pos, doc="Node positions of the system.")
+VolumeStateItem = _fixed_item("VolumeStateItem", "volume", lambda it: it.mmf.system.domain.volume, doc="Domain volume.")
+DomainStateItem = _fixed_item("DomainStateItem", "domain", lambda it: it.mmf.system.domain.rvecs, doc="Domain vectors.")
+TemperatureStateItem = _fixed_item(
+    "TemperatureStateItem", "temp", lambda it: getattr(it, "temp", None), attrs=lambda it: [("ndof", it.ndof)],
+    doc="Instantaneous temperature; the number of degrees of freedom travels as an attribute.")
+EPotContribStateItem = _fixed_item(
+    "EPotContribStateItem", "epot_contribs", lambda it: np.array([part.energy for part in it.mmf.parts]),
+    attrs=lambda it: [("epot_contrib_names", np.array([part.name for part in it.mmf.parts], dtype="S"))],
+    doc="Energy of every force part; the part names travel as an attribute.")
 
 
 class Iterative(object):
-    """Base of the iterative algorithms (iterative.py:41-105)."""
+    """Counter, hooks and state of an iterative algorithm; subclasses implement ``propagate`` (returning True to stop)."""
 
     default_state = []
     log_name = "ITER"
 
     def __init__(self, mmf, state=None, hooks=None, counter0=0):
         self.mmf = mmf
-        self.state_list = [item.copy() for item in self.default_state]
-        if state is not None:
-            self.state_list += state
-        self.state = dict((item.key, item) for item in self.state_list)
+        self.state_list = [item.copy() for item in self.default_state] + list(state or [])
+        self.state = {item.key: item for item in self.state_list}
         if hooks is None:
-            self.hooks = []
-        elif hasattr(hooks, "__len__"):
-            self.hooks = hooks
-        else:
-            self.hooks = [hooks]
+            hooks = []
+        elif not hasattr(hooks, "__len__"):
+            hooks = [hooks]
+        self.hooks = hooks
         self._add_default_hooks()
-        self.counter0 = counter0
-        self.counter = counter0
+        self.counter0 = self.counter = counter0
         self.initialize()
 
     def _add_default_hooks(self):
@@ -146,25 +130,23 @@ class Iterative(object):
     def initialize(self):
         self.call_hooks()
 
+    def _refresh_state(self):
+        for item in self.state_list:
+            item.update(self)
+
     def call_hooks(self):
-        state_updated = False
-        for hook in self.hooks:
-            if hook.expects_call(self.counter):
-                if not state_updated:
-                    for item in self.state_list:
-                        item.update(self)
-                    state_updated = True
-                hook(self)
+        firing = [hook for hook in self.hooks if hook.expects_call(self.counter)]
+        if firing:
+            self._refresh_state()  # once per iteration, and only when somebody looks
+        for hook in firing:
+            hook(self)
 
     def run(self, nsteps=None):
-        if nsteps is None:
-            while True:
-                if self.propagate():
-                    break
-        else:
-            for _ in range(nsteps):
-                if self.propagate():
-                    break
+        done = 0
+        while nsteps is None or done < nsteps:
+            done += 1
+            if self.propagate():
+                break
         self.finalize()
 
     def propagate(self):
