@@ -25,30 +25,40 @@ __all__ = [
 ]
 
 
-def _clean(iterative):
-    clean_momenta(iterative.pos, iterative.vel, iterative.masses, iterative.mmf.system.domain)
+class _HostThermostat(VerletHook):
+    """Common part of the thermostats that act on the host arrays: momentum cleaning and the default number of
+    degrees of freedom at ``init``; ``pre`` does the work unless a subclass also defines ``post``.  ``kind`` says whether
+    random numbers are involved; ``TBCombination`` and ``VerletIntegrator._verify_hooks`` look at ``method``."""
+
+    method = "thermostat"
+    sets_ndof = False      # fills in iterative.ndof (3N minus the conserved momenta) when the user gave none
+    always_cleans = True   # False: skip the momentum cleaning on a restart
+
+    def __init__(self, temp, start=0, step=1, timecon=None):
+        self.temp = temp
+        if timecon is not None:
+            self.timecon = timecon
+        VerletHook.__init__(self, start, step)
+
+    def init(self, iterative):
+        if self.always_cleans or not getattr(self, "restart", False):
+            clean_momenta(iterative.pos, iterative.vel, iterative.masses, iterative.mmf.system.domain)
+        if self.sets_ndof and iterative.ndof is None:
+            iterative.ndof = get_ndof_internal_md(iterative.pos.shape[0], iterative.mmf.system.domain.nvec)
+
+    def post(self, iterative, G1_add=None):
+        pass
 
 
-def _default_ndof(iterative):
-    if iterative.ndof is None:
-        iterative.ndof = get_ndof_internal_md(iterative.pos.shape[0], iterative.mmf.system.domain.nvec)
-
-
-class AndersenThermostat(VerletHook):
+class AndersenThermostat(_HostThermostat):
     """Velocities redrawn from the Maxwell-Boltzmann distribution every call (nvt.py:48-107)."""
 
     name = "Andersen"
     kind = "stochastic"
-    method = "thermostat"
 
     def __init__(self, temp, start=0, step=1, select=None, annealing=1.0):
-        self.temp = temp
-        self.select = select
-        self.annealing = annealing
-        VerletHook.__init__(self, start, step)
-
-    def init(self, iterative):
-        _clean(iterative)
+        _HostThermostat.__init__(self, temp, start, step)
+        self.select, self.annealing = select, annealing
 
     def pre(self, iterative, G1_add=None):
         before = iterative._compute_ekin()
@@ -56,31 +66,22 @@ class AndersenThermostat(VerletHook):
             iterative.vel[:] = get_random_vel(self.temp, False, iterative.masses)
         else:
             iterative.vel[self.select] = get_random_vel(self.temp, False, iterative.masses, self.select)
-        _clean(iterative)
+        clean_momenta(iterative.pos, iterative.vel, iterative.masses, iterative.mmf.system.domain)
         self.econs_correction += before - iterative._compute_ekin()
         self.temp *= self.annealing
 
-    def post(self, iterative, G1_add=None):
-        pass
 
-
-class BerendsenThermostat(VerletHook):
+class BerendsenThermostat(_HostThermostat):
     """Weak-coupling velocity rescaling (nvt.py:110-162)."""
 
     name = "Berendsen"
     kind = "deterministic"
-    method = "thermostat"
+    sets_ndof = True
+    always_cleans = False
 
     def __init__(self, temp, start=0, timecon=100 * femtosecond, restart=False):
-        self.temp = temp
-        self.timecon = timecon
+        _HostThermostat.__init__(self, temp, start, 1, timecon)
         self.restart = restart
-        VerletHook.__init__(self, start, 1)
-
-    def init(self, iterative):
-        if not self.restart:
-            _clean(iterative)
-        _default_ndof(iterative)
 
     def pre(self, iterative, G1_add=None):
         ekin = iterative.ekin
@@ -90,56 +91,43 @@ class BerendsenThermostat(VerletHook):
         iterative.ekin = iterative._compute_ekin()
         self.econs_correction += (1 - scale ** 2) * ekin
 
-    def post(self, iterative, G1_add=None):
-        pass
 
-
-class LangevinThermostat(VerletHook):
+class LangevinThermostat(_HostThermostat):
     """Half-step Ornstein-Uhlenbeck velocity update before and after the Verlet step (nvt.py:165-218); this is the
     thermostat ``simulations/md.py`` uses."""
 
     name = "Langevin"
     kind = "stochastic"
-    method = "thermostat"
 
     def __init__(self, temp, start=0, timecon=100 * femtosecond):
-        self.temp = temp
-        self.timecon = timecon
-        VerletHook.__init__(self, start, 1)
+        _HostThermostat.__init__(self, temp, start, 1, timecon)
 
-    def init(self, iterative):
-        _clean(iterative)
-
-    def _half_step(self, iterative):
-        before = iterative.ekin
+    def thermo(self, iterative):
         damp = np.exp(-iterative.timestep / self.timecon / 2)
         kick = np.sqrt((1.0 - damp ** 2) * self.temp * boltzmann / iterative.masses).reshape(-1, 1)
         iterative.vel[:] = damp * iterative.vel + kick * np.random.normal(0, 1, iterative.vel.shape)
         iterative.ekin = iterative._compute_ekin()
+
+    def _tracked(self, iterative, G1_add=None):
+        before = iterative.ekin
+        self.thermo(iterative)
         self.econs_correction += before - iterative.ekin
 
-    def pre(self, iterative, G1_add=None):
-        self._half_step(iterative)
-
-    def post(self, iterative, G1_add=None):
-        self._half_step(iterative)
+    pre = post = _tracked
 
 
-class CSVRThermostat(VerletHook):
+class CSVRThermostat(_HostThermostat):
     """Canonical sampling through stochastic velocity rescaling (nvt.py:221-274)."""
 
     name = "CSVR"
     kind = "stochastic"
-    method = "thermostat"
+    sets_ndof = True
 
     def __init__(self, temp, start=0, timecon=100 * femtosecond):
-        self.temp = temp
-        self.timecon = timecon
-        VerletHook.__init__(self, start, 1)
+        _HostThermostat.__init__(self, temp, start, 1, timecon)
 
     def init(self, iterative):
-        _clean(iterative)
-        _default_ndof(iterative)
+        _HostThermostat.init(self, iterative)
         self.kin = 0.5 * iterative.ndof * boltzmann * self.temp
 
     def pre(self, iterative, G1_add=None):
@@ -155,33 +143,28 @@ class CSVRThermostat(VerletHook):
         self.econs_correction += (1 - alpha ** 2) * iterative.ekin
         iterative.ekin = iterative.ekin_new
 
-    def post(self, iterative, G1_add=None):
-        pass
 
-
-class GLEThermostat(VerletHook):
+class GLEThermostat(_HostThermostat):
     """Coloured-noise (generalised Langevin) thermostat with ``ns`` auxiliary momenta per coordinate (nvt.py:277-358)."""
 
     name = "GLE"
     kind = "stochastic"
-    method = "thermostat"
 
     def __init__(self, temp, a_p, c_p=None, start=0):
-        self.temp = temp
+        _HostThermostat.__init__(self, temp, start, 1)
         self.ns = int(a_p.shape[0] - 1)
         self.a_p = a_p
         self.c_p = boltzmann * temp * np.eye(self.ns + 1) if c_p is None else c_p
-        VerletHook.__init__(self, start, 1)
 
     def init(self, iterative):
-        _clean(iterative)
+        _HostThermostat.init(self, iterative)
         self.s = 0.5 * boltzmann * self.temp * np.random.normal(size=(self.ns, iterative.pos.size))
         evals, evecs = np.linalg.eig(-self.a_p * iterative.timestep / 2)
         self.t = np.dot(evecs * np.exp(evals), np.linalg.inv(evecs)).real
         self.S = stabilized_cholesky_decomp(self.c_p - self.t @ self.c_p @ self.t.T).real
         self.n_atoms = iterative.pos.shape[0]
 
-    def thermo(self, iterative):
+    def thermo(self, iterative, G1_add=None):
         before = iterative.ekin
         root_m = np.sqrt(iterative.masses).reshape(-1, 1)
         old = np.vstack([(root_m * iterative.vel).reshape(-1), self.s])
@@ -191,11 +174,7 @@ class GLEThermostat(VerletHook):
         iterative.ekin = iterative._compute_ekin()
         self.econs_correction += before - iterative.ekin
 
-    def pre(self, iterative, G1_add=None):
-        self.thermo(iterative)
-
-    def post(self, iterative, G1_add=None):
-        self.thermo(iterative)
+    pre = post = thermo
 
 
 class NHChain(object):

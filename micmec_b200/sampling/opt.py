@@ -106,32 +106,32 @@ class CGOptimizer(BaseOptimizer):
 
 
 class HessianModel(object):
+    """Dense model of the Hessian, identity unless ``hessian0`` is given; subclasses implement the secant ``update``
+    and return False when they had to skip it."""
+
     def __init__(self, ndof, hessian0=None):
         self.ndof = ndof
-        if hessian0 is None:
-            self.hessian = np.identity(ndof, float)
-        else:
-            self.hessian = hessian0.copy()
-            if self.hessian.shape != (ndof, ndof):
-                raise TypeError("Incorrect shape of the initial hessian in quasi-newton method.")
+        self.hessian = np.identity(ndof, float) if hessian0 is None else hessian0.copy()
+        if self.hessian.shape != (ndof, ndof):
+            raise TypeError("Incorrect shape of the initial hessian in quasi-newton method.")
 
     def get_spectrum(self):
         return np.linalg.eigh(self.hessian)
 
+    def _add_rank_one(self, vec, scale):
+        self.hessian += np.outer(vec, vec) / scale
+
 
 class BFGSHessianModel(HessianModel):
     def update(self, dx, dg):
-        """Rank-two update; skipped (returns False) when either curvature is not safely positive (opt.py:208-236)."""
+        """Rank-two update; skipped when either curvature is not safely positive (opt.py:208-236)."""
         hdx = np.dot(self.hessian, dx)
         hmax = abs(self.hessian).max()
-        curv_model = np.dot(dx, hdx)
-        if hmax * curv_model <= 1e-5 * abs(hdx).max() ** 2:
+        curv_model, curv_true = np.dot(dx, hdx), np.dot(dg, dx)
+        if hmax * curv_model <= 1e-5 * abs(hdx).max() ** 2 or hmax * curv_true <= 1e-5 * abs(dg).max() ** 2:
             return False
-        curv_true = np.dot(dg, dx)
-        if hmax * curv_true <= 1e-5 * abs(dg).max() ** 2:
-            return False
-        self.hessian -= np.outer(hdx, hdx) / curv_model
-        self.hessian += np.outer(dg, dg) / curv_true
+        self._add_rank_one(hdx, -curv_model)
+        self._add_rank_one(dg, curv_true)
         return True
 
 
@@ -140,14 +140,15 @@ class SR1HessianModel(HessianModel):
         """Symmetric rank-one update; skipped when the denominator is tiny (opt.py:239-255)."""
         resid = dg - np.dot(self.hessian, dx)
         denom = np.dot(resid, dx)
-        if abs(denom) > 1e-5 * np.linalg.norm(dx) * np.linalg.norm(resid):
-            self.hessian += np.outer(resid, resid) / denom
-            return True
-        return False
+        if abs(denom) <= 1e-5 * np.linalg.norm(dx) * np.linalg.norm(resid):
+            return False
+        self._add_rank_one(resid, denom)
+        return True
 
 
 class QNOptimizer(BaseOptimizer):
-    """Trust-radius quasi-Newton optimiser (opt.py:258-393)."""
+    """Trust-radius quasi-Newton optimiser (opt.py:258-393): SR1 model, step from the model's spectrum inside the trust
+    radius, acceptance on an energy decrease (on a gradient-norm decrease once the radius is below ``small_radius``)."""
 
     log_name = "QNOPT"
 
@@ -155,15 +156,16 @@ class QNOptimizer(BaseOptimizer):
                  too_small_radius=1e-10, hessian0=None):
         self.x_old = dof.x0
         self.hessian = SR1HessianModel(len(dof.x0), hessian0)
-        self.trust_radius = trust_radius
-        self.initial_trust_radius = trust_radius
-        self.small_radius = small_radius
-        self.too_small_radius = too_small_radius
+        self.trust_radius = self.initial_trust_radius = trust_radius
+        self.small_radius, self.too_small_radius = small_radius, too_small_radius
         BaseOptimizer.__init__(self, dof, state, hooks, counter0)
+
+    def _advance(self):
+        self.x, self.f, self.g = self.make_step()
 
     def initialize(self):
         self.f_old, self.g_old = self.fun(self.dof.x0, True)
-        self.x, self.f, self.g = self.make_step()
+        self._advance()
         BaseOptimizer.initialize(self)
 
     def propagate(self):
@@ -172,29 +174,36 @@ class QNOptimizer(BaseOptimizer):
             self.hessian = SR1HessianModel(len(self.x))
             self.trust_radius = self.initial_trust_radius
         self.x_old, self.f_old, self.g_old = self.x, self.f, self.g
-        self.x, self.f, self.g = self.make_step()
+        self._advance()
         return BaseOptimizer.propagate(self)
+
+    def _rejects(self, f, g):
+        """Energy went up - or, at radii where energy differences drown in rounding, the gradient norm did."""
+        if f - self.f_old > 0:
+            return True
+        return self.trust_radius < self.small_radius and np.linalg.norm(g) - np.linalg.norm(self.g_old) > 0
+
+    def _shrink_below(self, radius):
+        """Halve the trust radius until it is strictly inside the step that was just rejected (opt.py:376-382)."""
+        self.trust_radius *= 0.5
+        while self.trust_radius >= radius:
+            self.trust_radius *= 0.5
+        if self.trust_radius < self.too_small_radius:
+            raise RuntimeError("The trust radius becomes too small. Is the potential energy surface smooth?")
 
     def make_step(self):
         evals, evecs = self.hessian.get_spectrum()
         grad_eigen = np.dot(evecs.T, self.g_old)
         while True:
             delta_eigen = solve_trust_radius(grad_eigen, evals, self.trust_radius)
-            radius = np.linalg.norm(delta_eigen)
             x = self.x_old + np.dot(evecs, delta_eigen)
             f, g = self.fun(x, True)
-            shrink = f - self.f_old > 0
-            if self.trust_radius < self.small_radius and np.linalg.norm(g) - np.linalg.norm(self.g_old) > 0:
-                shrink = True  # at tiny radii the energy difference drowns in rounding: watch the gradient norm
-            if not shrink:
-                if self.trust_radius < self.initial_trust_radius:
-                    self.trust_radius *= 2.0
-                return x, f, g
-            self.trust_radius *= 0.5
-            while self.trust_radius >= radius:
-                self.trust_radius *= 0.5
-            if self.trust_radius < self.too_small_radius:
-                raise RuntimeError("The trust radius becomes too small. Is the potential energy surface smooth?")
+            if self._rejects(f, g):
+                self._shrink_below(np.linalg.norm(delta_eigen))
+                continue
+            if self.trust_radius < self.initial_trust_radius:
+                self.trust_radius *= 2.0
+            return x, f, g
 
 
 def solve_trust_radius(grad, evals, radius, threshold=1e-5):
