@@ -91,6 +91,9 @@ def main(argv=None):
         sys.stderr.write(__doc__)
         return 2
     install()
+    from .log import log
+
+    log.set_level(log.medium)  # scripts print their progress tables, like the reference's default log level
     sys.argv = argv
     runpy.run_path(argv[0], run_name="__main__")
     return 0

@@ -21,13 +21,22 @@ __all__ = [
 
 
 class OptScreenLog(Hook):
-    """Convergence table on the screen (opt.py:52-84).  Silent unless ``verbose``."""
+    """Convergence table on the screen (opt.py:52-84).  Prints when ``verbose`` is True or, by default, when the
+    package log level is at least medium (see ``VerletScreenLog``)."""
 
-    def __init__(self, start=0, step=1, verbose=False):
+    def __init__(self, start=0, step=1, verbose=None):
         Hook.__init__(self, start, step)
         self.time0 = None
-        self.verbose = verbose
+        self._verbose = verbose
         self.lines = 0
+
+    @property
+    def verbose(self):
+        if self._verbose is None:
+            from ..log import log
+
+            return log.do_medium
+        return self._verbose
 
     def __call__(self, iterative):
         if self.time0 is None:

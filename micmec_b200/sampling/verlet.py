@@ -77,13 +77,23 @@ class VerletHook(Hook):
 
 
 class VerletScreenLog(Hook):
-    """Screen logger (verlet.py:342-374).  Silent unless ``verbose`` (the reference defers to its log level)."""
+    """Screen logger (verlet.py:342-374).  Prints when ``verbose`` is True, or - with ``verbose=None``, the default -
+    when the package log level is at least medium, as the reference does (``micmec_b200.log.log.set_level``; the level
+    is quiet by default and raised to medium by ``python -m micmec_b200.dropin``)."""
 
-    def __init__(self, start=0, step=1, verbose=False):
+    def __init__(self, start=0, step=1, verbose=None):
         Hook.__init__(self, start, step)
         self.time0 = None
-        self.verbose = verbose
+        self._verbose = verbose
         self.lines = 0
+
+    @property
+    def verbose(self):
+        if self._verbose is None:
+            from ..log import log
+
+            return log.do_medium
+        return self._verbose
 
     def __call__(self, iterative):
         if self.time0 is None:
