@@ -111,7 +111,6 @@ def _replica_worker(rank, world, port, out_dir):
     """One rank of a 'replicas only' run: optimise the own share, gather the energies on rank 0 (gloo)."""
     import os
 
-    import torch
     import torch.distributed as dist
     from micmec_b200.sampling.batchopt import ReplicaQNOptimizer, shard
 
