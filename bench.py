@@ -30,6 +30,12 @@ sys.path.insert(0, ROOT)
 
 BYTES_PER_NODE_STEP = 108.0   # pos r/w 48 + vel r/w 48 + mass 8 + cell type 4, per force-evaluation-step
 BYTES_PER_NODE_EVAL = 52.0    # force-only evaluation: pos 24 + type 4 + gpos 24
+FLOPS_PER_NODE_STEP = 600.0   # `original` model, one state: 0.55-0.65 kflop per cell and force evaluation (FMA = 2)
+BOLTZMANN = 3.1668154051341965e-06  # molmod.boltzmann (micmec_b200/units.py)
+# unmodified Python reference, single core, measured in the build container: NOT this host
+REFERENCE_PYTHON = {"value": 2.7e3, "unit": "node-steps/s", "cores": 1, "where": "build box, not this host",
+                    "what": "unmodified micmec (Python/NumPy) NPT NHC+MTK MD on data/4x4x4_fcu_micmec.chk, 50 steps: 42.5 steps/s "
+                            "(BASELINE.md section 2); NVE 3x3x3_test 1.03e4, NVT 5x5x5_fcu_hollow 3.2e4"}
 
 
 def parse_args():
@@ -54,18 +60,29 @@ def parse_args():
 FORCE_EVALS = {"nve": 1, "nvt": 1, "npt": 3}
 
 
+def global_fields(grid, seed=0, amp=0.1):
+    """Displacements and velocities of ALL G^3 nodes in reference order (id = (k*G + l)*G + m), NumPy only: `amp` bohr
+    Gaussian displacements and Maxwell-Boltzmann velocities at 300 K (the recipe of sampling/utils.get_random_vel) with
+    the centre-of-mass motion removed, from ONE seeded stream.  Every rank of a multi-GPU run draws the same global
+    arrays and keeps its z-slab, so N = 1, 2, 4 and 8 integrate the bit-identical initial state."""
+    from micmec_b200.celltypes import TYPE_FCU  # constants only (data/4x4x4_fcu_micmec.chk:365-398), pure Python
+
+    n = grid ** 3
+    rng = np.random.default_rng(seed)
+    dpos = amp * rng.standard_normal((n, 3))
+    vel = rng.standard_normal((n, 3)) * np.sqrt(BOLTZMANN * 300.0 / float(TYPE_FCU["mass"]))
+    vel -= vel.mean(axis=0)
+    return dpos, vel
+
+
 def make_state(grid, seed=0, amp=0.1, explicit=False):
-    """Synthetic G^3 fcu grid: rest lattice + `amp` bohr Gaussian displacement, Maxwell-Boltzmann velocities at
-    300 K with the centre-of-mass motion removed (same recipe as sampling/utils.get_random_vel, seeded)."""
+    """Synthetic G^3 fcu grid (one GPU): rest lattice + the global displacement / velocity fields."""
     from micmec_b200.system import System
     from micmec_b200.celltypes import TYPE_FCU
-    from micmec_b200.units import boltzmann
 
     system = System.periodic_grid((grid,) * 3, TYPE_FCU, explicit=explicit)
-    rng = np.random.default_rng(seed)
-    system.pos += amp * rng.standard_normal(system.pos.shape)
-    vel = rng.standard_normal(system.pos.shape) * np.sqrt(boltzmann * 300.0 / system.masses)[:, None]
-    vel -= vel.mean(axis=0)
+    dpos, vel = global_fields(grid, seed, amp)
+    system.pos += dpos
     return system, vel
 
 
@@ -125,16 +142,20 @@ class ClockSampler(threading.Thread):
 
 def cpu_oracle_rate(grid, ensemble, model, steps, nthreads, target_seconds=None):
     """node-steps/s of the CPU oracle port (test infrastructure; here it is only the thing being TIMED as the
-    reported CPU baseline, never the product path).  With target_seconds the step count is chosen from a two-step
-    pilot so that the timed run lasts about that long."""
+    reported CPU baseline, never the product path).  Its input is built with NumPy alone: nothing of the product
+    library is loaded by this leg.  With target_seconds the step count is chosen from a two-step pilot so that the
+    timed run lasts about that long."""
     from oracle import oracle as orc
+    from micmec_b200.celltypes import TYPE_FCU  # pure-Python constants
 
-    system, vel = make_state(grid, explicit=True)
+    arrays, pos, masses, rvecs = orc.periodic_grid_system((grid,) * 3, TYPE_FCU)
+    dpos, vel = global_fields(grid)
+    pos = pos + dpos
     p = md_params(ensemble)
-    o = orc.Oracle(system, model=model, nthreads=nthreads)
+    o = orc.Oracle(model=model, nthreads=nthreads, **arrays)
     thermo = dict(temp=p["temp"], timecon=p["timecon_thermo"], chain_vel0=p["chain_vel0"], chain_pos0=np.zeros(3)) if p["thermo"] else None
     baro = dict(temp=p["temp"], press=p["press"], timecon=p["timecon_baro"], vel_press0=p["vel_press0"]) if p["baro"] else None
-    md = o.md(system.pos, vel, system.masses, np.array(system.domain.rvecs), p["timestep"], thermo=thermo, baro=baro)
+    md = o.md(pos, vel, masses, rvecs, p["timestep"], thermo=thermo, baro=baro)
     md.run(1)
     if target_seconds:
         t0 = time.perf_counter()
@@ -143,23 +164,31 @@ def cpu_oracle_rate(grid, ensemble, model, steps, nthreads, target_seconds=None)
     t0 = time.perf_counter()
     md.run(steps)
     dt = time.perf_counter() - t0
-    return system.nnodes * steps / dt, dt, steps
+    return grid ** 3 * steps / dt, dt, steps
 
 
 def run_reference(args, rank, world):
-    """The reference's CPU implementation of the path = the pinned oracle port, all host threads."""
+    """The reference's CPU implementation of the path = the pinned oracle port (oracle/micmec_oracle.c), all host threads,
+    on a bounded sample grid of the same workload (the line's config names the grid it really ran)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     rate, dt, _ = cpu_oracle_rate(args.cpu_grid, args.ensemble, args.model, args.steps, cores)
     sample = "%d^3-cell fcu grid, %s, %d steps, OpenMP x%d (bounded sample of the %d^3 workload)" % (
         args.cpu_grid, args.ensemble.upper(), args.steps, cores, args.grid)
+    config = workload_config(args, world)
+    config["workload"] += "; THIS ARM RAN the bounded %d^3-cell sample of it on the host cores" % args.cpu_grid
+    config["sample_grid"] = args.cpu_grid
+    config["nodes_total"] = config["nodes_per_gpu"] = args.cpu_grid ** 3
+    config["parallelism"] = "CPU arm: OpenMP x%d, no GPU" % cores
+    config["cache"] = "host memory"
     line = {
         "impl": "reference", "metric": "MD node-steps/s (force+Verlet, fp64)", "value": rate, "unit": "node-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, world),
-        "cpu_baseline": {"value": rate, "unit": "node-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": config,
+        "cpu_baseline": {"value": rate, "unit": "node-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "reference_python": REFERENCE_PYTHON},
         "e2e": {"value": rate, "unit": "node-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -181,6 +210,11 @@ def workload_config(args, world, comm_mode=None):
         "nodes_total": args.grid ** 3, "nodes_per_gpu": args.grid ** 3 // world, "force_evals_per_step": FORCE_EVALS[args.ensemble], "model": args.model,
         "parallelism": "single GPU" if world == 1 else "%d z-slabs (one per GPU); %s" % (world, COMM_MODES.get(comm_mode, "CPU arm: no exchange")),
         "cache": "inputs larger than L2 (pos/vel/gpos %.0f MB each)" % (24.0 * args.grid ** 3 / 1e6),
+        # deviations from SURVEY.md 8(d), same work per step: MTK time constant 1e5 fs instead of the class default 1000 fs
+        # (the unmodified reference collapses the cell of these stiff systems within two steps at 1000 fs,
+        # tests/golden/make_golden.py), displacement amplitude 0.1 bohr instead of 0.05 h0
+        "initial_state": "global_fields(seed 0): 0.1 bohr Gaussian displacements, 300 K Maxwell-Boltzmann velocities, identical for every N",
+        "timecon_baro_fs": 1.0e5, "timecon_thermo_fs": 100.0,
     }
 
 
@@ -209,21 +243,21 @@ def main():
     p = md_params(args.ensemble)
     ndof = None
     if world == 1:
-        system, vel0 = make_state(args.grid, seed=rank)
+        system, vel0 = make_state(args.grid)
         nnodes = nglobal = system.nnodes
         part = ForcePartMechanical(system, model=args.model, device=local_rank, structured=False if args.generic else None)
     else:
-        # strong scaling: the SAME G^3 grid cut into `world` z-slabs, one per GPU; every rank generates only its slab
+        # strong scaling: the SAME G^3 grid, the SAME initial state (global_fields), cut into `world` z-slabs, one per GPU
         from micmec_b200 import slab as slabmod
         from micmec_b200.celltypes import TYPE_FCU
-        from micmec_b200.units import boltzmann
 
         layout = slabmod.SlabLayout((args.grid,) * 3, rank, world)
         system = slabmod.local_system(layout, TYPE_FCU)
-        rng = np.random.default_rng(1000 + rank)
-        system.pos += 0.1 * rng.standard_normal(system.pos.shape)
-        vel0 = rng.standard_normal(system.pos.shape) * np.sqrt(boltzmann * 300.0 / system.masses)[:, None]
-        vel0 -= vel0.mean(axis=0)
+        dpos, gvel = global_fields(args.grid)
+        ids = layout.global_ids()
+        system.pos += dpos[ids]
+        vel0 = np.ascontiguousarray(gvel[ids])
+        del dpos, gvel, ids
         nnodes, nglobal = system.nnodes, layout.nnodes_global
         ndof = 3 * nglobal - (3 if (p["thermo"] or p["baro"]) else 0)
         part = ForcePartMechanical(system, model=args.model, device=local_rank, slab=layout.slab_arg())
@@ -262,6 +296,8 @@ def main():
     # ---- device-resident value -------------------------------------------------------------------------------
     _lib.check(lib.mm_md_run(md, max(args.warmup, 3)))
     barrier()
+    scal1 = np.zeros(_lib.S_COUNT)
+    _lib.check(lib.mm_md_scalars(md, _lib.ptr(scal1)))
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = part.launches
@@ -280,6 +316,8 @@ def main():
     value = nglobal * args.steps / (ms * 1e-3)
     scal = np.zeros(_lib.S_COUNT)
     _lib.check(lib.mm_md_scalars(md, _lib.ptr(scal)))  # raises on NaN: a diverged run is not a measurement
+    rv_end = np.zeros(9)
+    _lib.check(lib.mm_md_get_state(md, None, None, None, _lib.MM_HOST, _lib.ptr(rv_end), None, None, None))
 
     # ---- roofline of the dominant kernel (event-bracketed launches, separate short run) ----------------------------
     _lib.check(lib.mm_set_option(part.handle, b"profile", 1))
@@ -294,6 +332,9 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    # measured FP64 FMA issue rate of a B200 SM (profiles/microbench/fp64_mio_probe_b200.txt): one warp-wide DFMA per
+    # 2.168 cycles and scheduler -> 148 SMs x 4 schedulers x 32 lanes x 2 flop / 2.168 x 1.965 GHz = 34.3 TFLOP/s
+    fp64_peak = 148 * 4 * 32 * 2 / 2.168 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
     # dominant kernel: the fused kick-drift-force-kick launch when the structured path is active (kind 1), else the
     # per-cell force kernel of the indexed path (kind 0).  Algorithmic bytes: SURVEY.md 8(d), per node and launch.
     fused = nl[1] > 0
@@ -302,26 +343,45 @@ def main():
     else:
         kernel_ms, name, bpn = tot[0] / max(nl[0], 1), "k_cells (per-cell force kernel, indexed topology)", BYTES_PER_NODE_EVAL
     achieved = bpn * nnodes / (kernel_ms * 1e-3) / 1e9
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this grid (single GPU), if any
-    traffic = None
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this grid and ensemble
+    # (single GPU), if any
+    traffic = traffic_src = None
+    caps = {}
     try:
         caps = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        cap = caps.get("%s@%d" % ("k_march_step" if fused else "k_cells", args.grid))
-        if cap and world == 1:
+        cap = caps.get("%s_%s@%d" % ("k_march_step" if fused else "k_cells", args.ensemble, args.grid))
+        if cap and world == 1 and args.model == "original":
             traffic = float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])
+            traffic_src = cap.get("kernel")
     except Exception:
         pass
+    flops = FLOPS_PER_NODE_STEP * nnodes
+    fp64_achieved = flops / (kernel_ms * 1e-3) / 1e12
+    t_hbm, t_fp64 = bpn * nnodes / (peak * 1e9), flops / (fp64_peak * 1e12)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "traffic_kernel": traffic_src,
         "kernel": name, "bytes_per_node": bpn, "kernel_ms": kernel_ms, "launches_timed": int(nl[1] if fused else nl[0]),
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
+        # the path sits on the FP64 ridge - report against min(HBM, FP64) with the MEASURED FMA peak
+        "fp64": {"peak_tflops": fp64_peak, "achieved_tflops": fp64_achieved, "frac": fp64_achieved / fp64_peak,
+                 "flops_per_node": FLOPS_PER_NODE_STEP,
+                 "peak_source": "measured DFMA issue rate, profiles/microbench/fp64_mio_probe_b200.txt"},
+        "binding": "fp64" if t_fp64 > t_hbm else "hbm",
+        "frac_of_binding_roofline": max(t_hbm, t_fp64) / (kernel_ms * 1e-3),
         # whole step against the survey's convention of 108 B per node and force evaluation
         "step_frac_of_108B_roofline": (BYTES_PER_NODE_STEP * FORCE_EVALS[args.ensemble] * nnodes * args.steps / (ms * 1e-3) / 1e9) / peak,
     }
     if fused and nl[0] > 0:  # the force-only launches of the barostat (52 B/node algorithmic)
         fms = tot[0] / nl[0]
         roofline["force_only_kernel"] = {"kernel": "k_march<FORCE>", "kernel_ms": fms, "bytes_per_node": BYTES_PER_NODE_EVAL,
-                                         "achieved": BYTES_PER_NODE_EVAL * nnodes / (fms * 1e-3) / 1e9, "launches_timed": int(nl[0])}
+                                         "achieved": BYTES_PER_NODE_EVAL * nnodes / (fms * 1e-3) / 1e9,
+                                         "frac": BYTES_PER_NODE_EVAL * nnodes / (fms * 1e-3) / 1e9 / peak,
+                                         "fp64_frac": FLOPS_PER_NODE_STEP * nnodes / (fms * 1e-3) / 1e12 / fp64_peak,
+                                         "launches_timed": int(nl[0])}
+        cap = caps.get("k_march_force_%s@%d" % (args.ensemble, args.grid))
+        if cap and world == 1 and args.model == "original":
+            roofline["force_only_kernel"]["traffic"] = float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])
 
     # ---- e2e: host buffers in, one step, host buffers out, every step ---------------------------------------------
     e2e = None
@@ -354,7 +414,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         rate, dt, csteps = cpu_oracle_rate(args.cpu_grid, args.ensemble, args.model, 3, cores, target_seconds=12.0)
-        cpu = {"value": rate, "unit": "node-steps/s", "cores": cores, "kind": "port",
+        cpu = {"value": rate, "unit": "node-steps/s", "cores": cores, "kind": "port", "reference_python": REFERENCE_PYTHON,
                "sample": "%d^3-cell fcu grid, %s, %d steps, OpenMP x%d, %.1f s" % (args.cpu_grid, args.ensemble.upper(), csteps, cores, dt)}
 
     if rank == 0:
@@ -365,7 +425,12 @@ def main():
             "config": workload_config(args, world, comm_mode), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
             "force_evals_per_s": value * FORCE_EVALS[args.ensemble],
-            "check": {"temp_K": scal[_lib.S_TEMP], "epot": scal[_lib.S_EPOT], "cons_err": scal[_lib.S_CONS_ERR]},
+            # identical initial state at every N (global_fields): these agree across N = 1, 2, 4, 8 to ~1e-10.
+            # econs_drift = |econs(after the timed steps) - econs(after the warm-up)| / ekin
+            "check": {"temp_K": scal[_lib.S_TEMP], "epot": scal[_lib.S_EPOT], "ekin": scal[_lib.S_EKIN],
+                      "econs": scal[_lib.S_ECONS], "rvecs": [float(x) for x in rv_end],
+                      "econs_drift": abs(scal[_lib.S_ECONS] - scal1[_lib.S_ECONS]) / scal[_lib.S_EKIN],
+                      "steps_total": int(scal[_lib.S_COUNTER])},
         }
         print(json.dumps(line))
     if world > 1:

@@ -114,6 +114,9 @@ int mm_synchronize(mm_handle *h);
 /* options: "scatter" 0 = node-centric gather (deterministic) / 1 = cell-centric warp-aggregated atomic scatter for
  * the gpos accumulation of the structured path; "profile" 1 = bracket every force kernel with CUDA events */
 int mm_set_option(mm_handle *h, const char *name, int64_t value);
+/* read back a setting or a derived launch parameter: "structured" (1 = the structured-grid kernels are active),
+ * "chunk" (planes per block along z), "rows_per_thread", "tile_rows", "blocks", "mass_uniform"; -1 for unknown names */
+int64_t mm_get_option(const mm_handle *h, const char *name);
 /* with "profile" on: launches timed since the last call and their summed device time (ms), separately for
  * [0] force-only kernels and [1] fused kick-drift-force-kick kernels; synchronises the stream and resets the counters */
 int mm_profile(mm_handle *h, int64_t nlaunch[2], double total_ms[2]);
@@ -159,6 +162,8 @@ typedef struct {
     int32_t has_baro;
     int32_t anisotropic, vol_constraint;
     double baro_temp, baro_press, baro_timecon;
+    double time0;      /* VerletIntegrator(time0=...), verlet.py:96: simulation time at initialisation (restarts) */
+    int64_t counter0;  /* VerletIntegrator(counter0=...), iterative.py: step counter at initialisation */
 } mm_md_desc;
 
 int mm_md_create(mm_handle *h, const mm_md_desc *desc, mm_md **out);
@@ -195,6 +200,7 @@ int mm_md_get_state(mm_md *md, double *pos, double *vel, double *gpos, int where
 #define MM_S_VTENS 16  /* 9 values */
 #define MM_S_PTENS 25  /* 9 values */
 #define MM_S_NFORCE 34 /* force evaluations so far */
+#define MM_S_CE_N 35   /* ConsErrTracker (verlet.py:275-307): counter, ekin_m, ekin_s, econs_m, econs_s */
 #define MM_S_COUNT 40
 int mm_md_scalars(mm_md *md, double *out /* [MM_S_COUNT] */);
 

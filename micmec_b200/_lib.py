@@ -20,12 +20,12 @@ MODELS = {"original": 0, "default": 1}
 # indices into the array filled by mm_md_scalars
 S_EPOT, S_EKIN, S_TEMP, S_ETOT, S_ECONS, S_CONS_ERR, S_PRESS, S_RMSD_GPOS, S_RMSD_DELTA = range(9)
 S_TIME, S_COUNTER, S_VOLUME, S_NDOF, S_ECONS_CORR = 9, 10, 11, 12, 13
-S_VTENS, S_PTENS, S_NFORCE, S_COUNT = 16, 25, 34, 40
+S_VTENS, S_PTENS, S_NFORCE, S_CE_N, S_COUNT = 16, 25, 34, 35, 40
 
 EXPORTS = [
     "mm_create", "mm_destroy", "mm_last_error", "mm_version", "mm_device_ok", "mm_set_pos", "mm_set_rvecs",
     "mm_compute", "mm_get_cell_cache", "mm_launch_count", "mm_device_ptr", "mm_set_stream", "mm_synchronize",
-    "mm_set_option", "mm_profile", "mm_batched_eigh", "mm_set_rvecs_batch", "mm_get_replica_results", "mm_comm_unique_id", "mm_comm_init", "mm_comm_destroy", "mm_comm_mode", "mm_domain", "mm_md_create", "mm_md_destroy", "mm_md_init", "mm_md_set_state", "mm_md_run", "mm_md_get_state",
+    "mm_set_option", "mm_get_option", "mm_profile", "mm_batched_eigh", "mm_set_rvecs_batch", "mm_get_replica_results", "mm_comm_unique_id", "mm_comm_init", "mm_comm_destroy", "mm_comm_mode", "mm_domain", "mm_md_create", "mm_md_destroy", "mm_md_init", "mm_md_set_state", "mm_md_run", "mm_md_get_state",
     "mm_md_scalars",
 ]
 
@@ -71,6 +71,8 @@ class MDDesc(ctypes.Structure):
         ("baro_temp", ctypes.c_double),
         ("baro_press", ctypes.c_double),
         ("baro_timecon", ctypes.c_double),
+        ("time0", ctypes.c_double),
+        ("counter0", ctypes.c_int64),
     ]
 
 
@@ -104,6 +106,8 @@ def load():
     lib.mm_set_stream.argtypes = [vp, vp]
     lib.mm_synchronize.argtypes = [vp]
     lib.mm_set_option.argtypes = [vp, ctypes.c_char_p, i64]
+    lib.mm_get_option.argtypes = [vp, ctypes.c_char_p]
+    lib.mm_get_option.restype = i64
     lib.mm_profile.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(dbl)]  # int64[2], double[2]
     lib.mm_set_rvecs_batch.argtypes = [vp, vp]
     lib.mm_get_replica_results.argtypes = [vp, vp, vp]

@@ -400,6 +400,16 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value) {
     return invalid(std::string("mm_set_option: unknown option ") + name);
 }
 
+int64_t mm_get_option(const mm_handle *h, const char *name) {
+    if (!h || !name) return -1;
+    if (strcmp(name, "structured") == 0) return h->sg.active ? 1 : 0;
+    if (strcmp(name, "chunk") == 0) return h->sg.chunk;
+    if (strcmp(name, "tile_rows") == 0) return h->sg.tile_rows;
+    if (strcmp(name, "blocks") == 0) return h->sg.nblocks;
+    if (strcmp(name, "variant") == 0) return h->sg.variant;
+    return -1;
+}
+
 int mm_profile(mm_handle *h, int64_t *nlaunch, double *total_ms) {
     if (!h || !nlaunch || !total_ms) return invalid("mm_profile: null argument");
     MM_CUDA(cudaSetDevice(h->device));

@@ -857,6 +857,8 @@ int mm_md_init(mm_md *md, const double *pos, const double *vel, const double *ma
     s.boltzmann = h->boltzmann;
     s.timestep = d.timestep;
     s.ndof = d.ndof;
+    s.time = d.time0;  // verlet.py:96 / iterative.py: a restarted run continues its clock and its step counter
+    s.counter = d.counter0;
     for (int i = 0; i < 9; i++) {
         s.rvecs[i] = rvecs9[i];
         s.Mvel[i] = s.Rpos[i] = s.Rpend[i] = (i % 4 == 0) ? 1.0 : 0.0;
@@ -1076,6 +1078,11 @@ int mm_md_scalars(mm_md *md, double *out) {
         out[MM_S_PTENS + i] = s.ptens[i];
     }
     out[MM_S_NFORCE] = (double)s.nforce;
+    out[MM_S_CE_N] = (double)s.ce_n;
+    out[MM_S_CE_N + 1] = s.ce_ekin_m;
+    out[MM_S_CE_N + 2] = s.ce_ekin_s;
+    out[MM_S_CE_N + 3] = s.ce_econs_m;
+    out[MM_S_CE_N + 4] = s.ce_econs_s;
     // the reference raises from inside compute() (mmff.py:135-147); here the flag surfaces with the scalars
     if (std::isnan(s.epot) || std::isnan(s.ekin)) {
         set_error("The energy is not-a-number (``nan``).");

@@ -195,6 +195,11 @@ class ForcePartMechanical(ForcePart):
         return self._handle
 
     @property
+    def structured(self):
+        """True when the structured-grid (marching) kernels evaluate this part."""
+        return int(self._lib.mm_get_option(self._handle, b"structured")) == 1
+
+    @property
     def launches(self):
         """Number of CUDA kernels launched by this part so far."""
         return int(self._lib.mm_launch_count(self._handle))

@@ -373,12 +373,22 @@ class MTKAttributeStateItem(StateItem):
         self.attr = attr
 
     def get_value(self, iterative):
+        """npt.py:765-782: the first MTK barostat (bare or inside the first ``TBCombination``); ``chain_pos`` /
+        ``chain_vel`` come from the barostat's own thermostat chain (0 without one)."""
+        found = None
         for hook in iterative.hooks:
             if isinstance(hook, MTKBarostat):
-                return getattr(hook, self.attr)
-            if isinstance(hook, TBCombination) and isinstance(hook.barostat, MTKBarostat):
-                return getattr(hook.barostat, self.attr)
-        raise TypeError("Iterative does not contain an MTKBarostat hook.")
+                found = hook
+                break
+            if isinstance(hook, TBCombination):
+                found = hook.barostat if isinstance(hook.barostat, MTKBarostat) else None
+                break
+        if found is None:
+            raise TypeError("Iterative does not contain an MTKBarostat hook.")
+        if self.key.startswith("baro_chain_"):
+            chain_attr = self.key.split("_")[2]
+            return getattr(found.baro_thermo.chain, chain_attr) if found.baro_thermo is not None else 0
+        return getattr(found, self.attr)
 
     def copy(self):
         return self.__class__(self.attr)

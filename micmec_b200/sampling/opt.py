@@ -86,20 +86,87 @@ class BaseOptimizer(Iterative):
         self.dof.log()
 
 
+class _CGMinimizer(object):
+    """Self-contained nonlinear conjugate gradients with a Newton line search: the algorithm family the reference
+    borrows from ``molmod.minimizer`` (``Minimizer(x0, fun, ConjugateGradient(), NewtonLineSearch(), ...)``,
+    opt.py:160-164).  molmod is not vendored with the reference, so this is a restatement of the published scheme, not
+    a line-by-line mirror (parity with molmod's iterates is unpinned; the minimum it converges to is tested):
+
+    * search direction: Polak-Ribiere with automatic restart, ``beta = max(0, g.(g - g_old) / g_old.g_old)``;
+      the first step and every restart are steepest descent;
+    * line search: one Newton step along the unit direction, with the curvature from a finite difference of the
+      ANALYTIC gradient, ``f'' ~ (g(x + eps d) - g(x)).d / eps``; the step is limited to ``qmax`` and halved until the
+      function decreases; a non-positive curvature falls back to a step of length ``qmax``;
+    * a failed line search along a conjugate direction restarts with steepest descent; a failed steepest-descent line
+      search ends the minimisation (``propagate`` returns False), as in the reference's wiring.
+    """
+
+    def __init__(self, x0, fun, eps=1e-6, qmax=1.0, max_halvings=20):
+        self.x = np.array(x0, dtype=float)
+        self.fun = fun
+        self.eps, self.qmax, self.max_halvings = eps, qmax, max_halvings
+        self.f = self.gradient = self.direction = self.gradient_old = None
+        self.status = "SD"
+
+    def initialize(self):
+        self.f, self.gradient = self.fun(self.x, do_gradient=True)
+        self.gradient = np.array(self.gradient, dtype=float)
+        self.direction = -self.gradient
+        self.status = "SD"
+
+    def _line_search(self):
+        norm = np.linalg.norm(self.direction)
+        if norm == 0.0:
+            return False
+        unit = self.direction / norm
+        slope = np.dot(self.gradient, unit)
+        if slope >= 0.0:
+            return False  # not a descent direction
+        _, g_eps = self.fun(self.x + self.eps * unit, do_gradient=True)
+        curvature = (np.dot(g_eps, unit) - slope) / self.eps
+        step = -slope / curvature if curvature > 0.0 else self.qmax
+        step = min(step, self.qmax)
+        for _ in range(self.max_halvings):
+            xnew = self.x + step * unit
+            fnew, gnew = self.fun(xnew, do_gradient=True)
+            if np.isfinite(fnew) and fnew < self.f:
+                self.x, self.f = xnew, fnew
+                self.gradient_old, self.gradient = self.gradient, np.array(gnew, dtype=float)
+                return True
+            step *= 0.5
+        return False
+
+    def propagate(self):
+        if not self._line_search():
+            if self.status == "SD":
+                return False
+            self.direction, self.status = -self.gradient, "SD"  # restart along the gradient
+            if not self._line_search():
+                return False
+        denom = np.dot(self.gradient_old, self.gradient_old)
+        beta = max(0.0, np.dot(self.gradient, self.gradient - self.gradient_old) / denom) if denom > 0.0 else 0.0
+        self.direction = -self.gradient + beta * self.direction
+        self.status = "CG" if beta > 0.0 else "SD"
+        return True
+
+
 class CGOptimizer(BaseOptimizer):
-    """Conjugate gradients with a Newton line search (opt.py:147-180).  The algorithm lives in ``molmod.minimizer``
-    (an external dependency of the reference); this class wires it up when molmod is installed."""
+    """Conjugate gradients with a Newton line search (opt.py:147-180).  The reference delegates the algorithm to
+    ``molmod.minimizer``; when molmod is importable that implementation is used (identical iterates), otherwise the
+    self-contained ``_CGMinimizer`` above - so ``simulations/relaxed_scan.py`` runs through the drop-in either way."""
 
     log_name = "CGOPT"
 
     def __init__(self, dof, state=None, hooks=None, counter0=0):
         try:
             from molmod.minimizer import ConjugateGradient, NewtonLineSearch, Minimizer
-        except ImportError as exc:
-            raise ImportError("CGOptimizer needs molmod.minimizer (a dependency of the reference); "
-                              "use QNOptimizer, which is self-contained.") from exc
-        self.minimizer = Minimizer(dof.x0, self.fun, ConjugateGradient(), NewtonLineSearch(), None, None, anagrad=True,
-                                   verbose=False)
+
+            if not hasattr(Minimizer, "propagate"):  # the test stand-in of molmod has no algorithm behind it
+                raise ImportError("molmod.minimizer stub")
+            self.minimizer = Minimizer(dof.x0, self.fun, ConjugateGradient(), NewtonLineSearch(), None, None,
+                                       anagrad=True, verbose=False)
+        except ImportError:
+            self.minimizer = _CGMinimizer(dof.x0, self.fun)
         BaseOptimizer.__init__(self, dof, state, hooks, counter0)
 
     def initialize(self):

@@ -213,6 +213,7 @@ class VerletIntegrator(Iterative):
         desc = _lib.MDDesc()
         desc.timestep = self.timestep
         desc.ndof = float(self.ndof)
+        desc.time0, desc.counter0 = float(self.time), int(self.counter)
         if thermo is not None:
             desc.has_thermo, desc.chain_length = 1, thermo.chain.length
             desc.thermo_temp, desc.thermo_timecon = thermo.chain.temp, thermo.chain.timecon
@@ -257,6 +258,10 @@ class VerletIntegrator(Iterative):
         self.vtens = out[_lib.S_VTENS:_lib.S_VTENS + 9].reshape(3, 3).copy()
         self.ptens = out[_lib.S_PTENS:_lib.S_PTENS + 9].reshape(3, 3).copy()
         self.nforce = int(out[_lib.S_NFORCE])
+        # the tracker and the per-part energies live on the device in this mode: mirror them for the state items
+        tracker = self._cons_err_tracker
+        tracker.counter = int(out[_lib.S_CE_N])
+        tracker.ekin_m, tracker.ekin_s, tracker.econs_m, tracker.econs_s = out[_lib.S_CE_N + 1:_lib.S_CE_N + 5]
         econs_corr = out[_lib.S_ECONS_CORR]
         rv, vp = np.zeros((3, 3)), np.zeros((3, 3))
         thermo, baro = self._thermo, self._baro
@@ -269,6 +274,7 @@ class VerletIntegrator(Iterative):
                                              _lib.ptr(cpos), _lib.ptr(cvel), _lib.ptr(vp)))
         if arrays:
             self.mmf.update_pos(self.pos)
+        part_energy = self.epot  # device mode runs a single force part (_native_setup)
         if baro is not None:
             self.rvecs = rv[: self.rvecs.shape[0]].copy()
             self.mmf.update_rvecs(np.ascontiguousarray(self.rvecs))
@@ -282,6 +288,7 @@ class VerletIntegrator(Iterative):
         for hook in self._verlet_hooks():
             if hook.name == "TBCombination":
                 hook.econs_correction = econs_corr
+        self._part.energy = self.mmf.energy = part_energy  # after update_pos / update_rvecs cleared the caches
         self._arrays_fresh = arrays
 
     def _steps_to_next_call(self, limit):

@@ -205,6 +205,35 @@ def cell_shifts(grid, surrounding_nodes, pbc=True):
     return shift
 
 
+def periodic_grid_system(shape, type_params):
+    """Full periodic ``nx x ny x nz`` grid of one cell type at rest, NumPy only (conventions of ``build_system``,
+    micmec/utils.py:164-263: node (k, l, m) has id ``(k*ny + l)*nz + m`` and sits at ``(k, l, m) * diag(h0)``,
+    ``rvecs = shape * diag(h0)``, node mass = 8 * 1/8 of the type mass).  Returns the keyword arguments of
+    ``Oracle`` plus ``pos``, ``masses``, ``rvecs``; used by the CPU arm of ``bench.py``, which must not load
+    anything of the product library."""
+    nx, ny, nz = (int(s) for s in shape)
+    k, l, m = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    k, l, m = k.ravel(), l.ravel(), m.ravel()
+    offsets = -_NEIGHBOR_CELLS  # vertex offsets (utils.py:43-52)
+
+    def ident(a, b, c):
+        return ((a % nx) * ny + (b % ny)) * nz + (c % nz)
+
+    sn = np.stack([ident(k + d[0], l + d[1], m + d[2]) for d in offsets], axis=1).astype(np.int64)
+    sc = np.stack([ident(k - d[0], l - d[1], m - d[2]) for d in offsets], axis=1).astype(np.int64)
+    # image shifts: vertex offset bit along an axis where the cell sits on the last layer (SURVEY.md App. A.1)
+    last = np.stack([k == nx - 1, l == ny - 1, m == nz - 1], axis=1)
+    shift = (last[:, None, :] & (offsets[None, :, :] == 1)).astype(np.int8)
+    h0 = np.asarray(type_params["cell"], dtype=float).reshape(-1, 3, 3)[0]
+    diag = np.diag(h0)
+    pos = np.stack([k * diag[0], l * diag[1], m * diag[2]], axis=1).astype(float)
+    n = nx * ny * nz
+    params = {"type1/" + key: type_params[key] for key in ("cell", "elasticity", "free_energy", "effective_temp", "mass")}
+    arrays = dict(surrounding_nodes=sn, surrounding_cells=sc, shift=shift, grid=np.ones((nx, ny, nz), dtype=np.int64),
+                  types=np.ones(n, dtype=np.int64), params=params, pbc=True)
+    return arrays, pos, np.full(n, float(type_params["mass"])), np.diag(np.array([nx, ny, nz], dtype=float) * diag)
+
+
 def type_tables(params, types):
     """Flatten ``system.params`` the way mmff.py:219-231 + :374-379 read it.  Returns compact arrays."""
     type_ids = sorted({int(t) for t in np.asarray(types).ravel()})

@@ -4,7 +4,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tests/multigpu_check.py
 
-Every rank integrates its slab of a perturbed 40 x 24 x 32 fcu grid (NVE, NVT and NPT, 30 steps); rank 0
+Every rank integrates its slab of a perturbed 40 x 24 x 32 fcu grid ($MULTIGPU_SHAPE; 40 x 24 x 64 for 8 slabs) (NVE, NVT and NPT, 30 steps); rank 0
 additionally runs the WHOLE grid on its own GPU with the same kernels.  Gathered positions / velocities and all
 scalars must agree to 1e-12 (the only difference is the order of the 16-double reductions).
 Prints "multigpu ok" on success.
@@ -51,7 +51,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    shape = (40, 24, 32)
+    shape = tuple(int(v) for v in os.environ.get("MULTIGPU_SHAPE", "40,24,32").split(","))
     rng = np.random.default_rng(11)  # same stream on every rank: everybody knows the global arrays
     full = System.periodic_grid(shape, TYPE_FCU, explicit=False)
     pos = full.pos + 0.3 * rng.standard_normal(full.pos.shape)

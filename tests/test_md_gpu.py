@@ -240,3 +240,27 @@ def test_host_driven_mode_for_foreign_verlet_hooks():
     assert gio.rel_rms(verlet.pos, d["step10:pos"]) <= 1e-9
     assert gio.rel_rms(verlet.vel, d["step10:vel"]) <= 1e-9
     assert abs(verlet.econs - float(d["step10:econs"])) <= 1e-9 * abs(float(d["step10:econs"]))
+
+
+def test_restart_continues_time_and_counter_in_device_mode():
+    """VerletIntegrator(time0=..., counter0=...) (verlet.py:96, iterative.py): a restarted device-resident run continues
+    the clock and the step counter instead of starting from zero, and its tracker / part energies are mirrored."""
+    from micmec_b200.sampling.verlet import VerletIntegrator
+    from micmec_b200.pes.mmff import MicMecForceField, ForcePartMechanical
+    from micmec_b200.sampling.iterative import ConsErrStateItem, EPotContribStateItem
+
+    d = gio.load("traj_" + gio.traj_fixtures()[0])
+    system = make_system(d)
+    system.pos[:] = d["init:pos"]
+    mmf = MicMecForceField(system, [ForcePartMechanical(system)])
+    dt = float(d["meta:timestep"])
+    verlet = VerletIntegrator(mmf, timestep=dt, vel0=d["init:vel"], time0=123.0 * dt, counter0=123)
+    assert verlet.device_mode
+    assert verlet.time == 123.0 * dt and verlet.counter == 123
+    verlet.run(7)
+    assert verlet.counter == 130
+    assert abs(verlet.time - 130.0 * dt) <= 1e-12 * 130.0 * dt
+    assert ConsErrStateItem("counter").get_value(verlet) == 8  # initial sample + 7 steps
+    assert ConsErrStateItem("ekin_m").get_value(verlet) > 0.0
+    contribs = EPotContribStateItem().get_value(verlet)
+    assert contribs.shape == (1,) and abs(contribs[0] - verlet.epot) <= 1e-12 * abs(verlet.epot)

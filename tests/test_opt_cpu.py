@@ -56,3 +56,22 @@ def test_hessian_models():
         assert not model.update(np.zeros(6), np.zeros(6))
     with pytest.raises(TypeError):
         SR1HessianModel(3, np.eye(4))
+
+
+@pytest.mark.parametrize("tag", ["cartesian_3x3x3_conf0", "strain_3x3x3_test"])
+def test_cg_optimizer_converges_to_the_reference_minimum(tag):
+    """CGOptimizer (opt.py:147-180) on the self-contained conjugate-gradient minimiser: molmod.minimizer is not in the
+    reference tree, so the iterates are not pinned; the minimum is - it must be the one the reference's QNOptimizer
+    run ended in."""
+    import goldenio as gio
+    from micmec_b200.sampling.opt import CGOptimizer
+
+    d, mmf, dof = optcases.build(tag, lambda system: OracleForcePart(system))
+    opt = CGOptimizer(dof)
+    f0 = float(d["iter0:f"])
+    opt.run(400)
+    assert dof.converged
+    last = "iter%d:" % int(d["meta:iterations"])
+    assert opt.epot <= float(d[last + "f"]) + 1e-7 * abs(f0)
+    assert gio.rel_rms(mmf.system.pos, d[last + "pos"]) <= 1e-4
+    assert gio.rel_rms(np.array(mmf.system.domain.rvecs), d[last + "rvecs"]) <= 1e-5
