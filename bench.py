@@ -53,6 +53,14 @@ def parse_args():
     ap.add_argument("--tile-rows", type=int, default=0, help="tuning: warps per block of the marching kernel (8/12/16)")
     ap.add_argument("--variant", type=int, default=-1, help="tuning bits of the marching kernel (1 pairwise barriers, 2 TMA loads, 4 two planes per trip, 8 one barrier per plane)")
     ap.add_argument("--chunk", type=int, default=0, help="tuning: planes per block along z")
+    ap.add_argument("--rpt", type=int, default=0, help="tuning: node rows per thread of k_march2 (1/2/3)")
+    ap.add_argument("--wrap", type=int, default=-1, help="tuning: 0 = k_march2 reads the periodic images from the ghost nodes")
+    ap.add_argument("--unroll", type=int, default=-1, help="tuning: planes per trip of k_march2's steady loop (1/2)")
+    ap.add_argument("--tail-in-kernel", type=int, default=-1, help="tuning: 1 = the last block of a marching launch runs the tail")
+    ap.add_argument("--tail", type=int, default=-1, help="tuning: 0 = reduction / exchange / scalar algebra in their own launches")
+    ap.add_argument("--pin-step", type=int, default=-1, help="tuning: 0 / 3 rows of Bq in per-thread registers, STEP launches")
+    ap.add_argument("--pin-force", type=int, default=-1, help="tuning: likewise for the force-only launches")
+    ap.add_argument("--march2", type=int, default=-1, help="tuning: 0 = keep the general kernel k_march for the one-type grids too")
     ap.add_argument("--generic", action="store_true", help="force the indexed-topology kernels (no structured path)")
     return ap.parse_args()
 
@@ -202,7 +210,7 @@ COMM_MODES = {
 }
 
 
-def workload_config(args, world, comm_mode=None):
+def workload_config(args, world, comm_mode=None, tiling=None):
     return {
         "workload": "synthetic %dx%dx%d-cell fcu grid %s MD (%s), dt 10 fs" % (
             args.grid, args.grid, args.grid, args.ensemble.upper(),
@@ -210,6 +218,7 @@ def workload_config(args, world, comm_mode=None):
         "nodes_total": args.grid ** 3, "nodes_per_gpu": args.grid ** 3 // world, "force_evals_per_step": FORCE_EVALS[args.ensemble], "model": args.model,
         "parallelism": "single GPU" if world == 1 else "%d z-slabs (one per GPU); %s" % (world, COMM_MODES.get(comm_mode, "CPU arm: no exchange")),
         "cache": "inputs larger than L2 (pos/vel/gpos %.0f MB each)" % (24.0 * args.grid ** 3 / 1e6),
+        "kernel_tiling": tiling,
         # deviations from SURVEY.md 8(d), same work per step: MTK time constant 1e5 fs instead of the class default 1000 fs
         # (the unmodified reference collapses the cell of these stiff systems within two steps at 1000 fs,
         # tests/golden/make_golden.py), displacement amplitude 0.1 bohr instead of 0.05 h0
@@ -261,6 +270,13 @@ def main():
         nnodes, nglobal = system.nnodes, layout.nnodes_global
         ndof = 3 * nglobal - (3 if (p["thermo"] or p["baro"]) else 0)
         part = ForcePartMechanical(system, model=args.model, device=local_rank, slab=layout.slab_arg())
+    if args.march2 >= 0:
+        _lib.check(lib.mm_set_option(part.handle, b"march2", args.march2))
+    if args.rpt:
+        _lib.check(lib.mm_set_option(part.handle, b"rows_per_thread", args.rpt))
+    for name, val in (("wrap_on_load", args.wrap), ("unroll", args.unroll), ("tail", args.tail), ("tail_in_kernel", args.tail_in_kernel), ("pin_step", args.pin_step), ("pin_force", args.pin_force)):
+        if val >= 0:
+            _lib.check(lib.mm_set_option(part.handle, name.encode(), val))
     if args.tile_rows:
         _lib.check(lib.mm_set_option(part.handle, b"tile_rows", args.tile_rows))
     if args.chunk:
@@ -286,6 +302,10 @@ def main():
         hooks.append(thermo)
     verlet = VerletIntegrator(mmf, timestep=p["timestep"], hooks=hooks, vel0=vel0, ndof=ndof)
     assert verlet.device_mode
+    opt = lambda name: int(lib.mm_get_option(part.handle, name))
+    tiling = {"kernel": "k_march2" if opt(b"march2") == 1 else "k_march", "rows_per_thread": opt(b"rows_per_thread"),
+              "warps": opt(b"tile_rows"), "chunk_planes": opt(b"chunk"), "blocks": opt(b"blocks"),
+              "images_on_load": opt(b"wrap_on_load"), "tail": {0: "separate reduction / scalar / halo launches", 1: "one tail launch", 2: "in the marching kernel"}[opt(b"tail")]}
     md = verlet._md
 
     def barrier():
@@ -422,7 +442,7 @@ def main():
             "metric": "MD node-steps/s (force+Verlet, fp64)", "value": value, "unit": "node-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world, comm_mode), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "config": workload_config(args, world, comm_mode, tiling), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
             "force_evals_per_s": value * FORCE_EVALS[args.ensemble],
             # identical initial state at every N (global_fields): these agree across N = 1, 2, 4, 8 to ~1e-10.

@@ -390,11 +390,42 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value) {
         if (!h->sg.d_sc) return MM_OK;
         MM_CUDA(cudaSetDevice(h->device));
         MM_CUDA(cudaStreamSynchronize(h->stream));
-        if (sg_set_tile_rows(h, (int)value) != MM_OK) return invalid("mm_set_option: tile_rows must be 8");
+        if (sg_set_tile_rows(h, (int)value) != MM_OK) return invalid("mm_set_option: tile_rows not compiled into this library");
+        return MM_OK;
+    }
+    if (strcmp(name, "rows_per_thread") == 0 || strcmp(name, "march2") == 0) {
+        if (!h->sg.d_sc) return MM_OK;
+        MM_CUDA(cudaSetDevice(h->device));
+        MM_CUDA(cudaStreamSynchronize(h->stream));
+        const int rc = name[0] == 'r' ? sg_set_rpt(h, (int)value) : sg_set_march2(h, (int)value);
+        if (rc != MM_OK) return invalid("mm_set_option: rows_per_thread / march2 configuration not compiled into this library");
         return MM_OK;
     }
     if (strcmp(name, "profile") == 0) {
         h->profile = value ? 1 : 0;
+        return MM_OK;
+    }
+    if (strcmp(name, "tail") == 0) {
+        h->sg.tail_wanted = value ? 1 : 0;
+        return MM_OK;
+    }
+    if (strcmp(name, "unroll") == 0) {
+        h->sg.unroll = value == 2 ? 2 : 1;
+        return MM_OK;
+    }
+    if (strcmp(name, "wrap_on_load") == 0) {
+        h->sg.wrap_wanted = value < 0 ? -1 : (value ? 1 : 0);
+        if (!h->sg.d_sc) return MM_OK;
+        MM_CUDA(cudaSetDevice(h->device));
+        MM_CUDA(cudaStreamSynchronize(h->stream));
+        return sg_retile(h, 0);
+    }
+    if (strcmp(name, "tail_in_kernel") == 0) {
+        h->sg.tail_in_kernel = value ? 1 : 0;
+        return MM_OK;
+    }
+    if (strcmp(name, "pin_step") == 0 || strcmp(name, "pin_force") == 0) {
+        (name[4] == 's' ? h->sg.pin_step : h->sg.pin_force) = value ? 3 : 0;
         return MM_OK;
     }
     return invalid(std::string("mm_set_option: unknown option ") + name);
@@ -407,6 +438,11 @@ int64_t mm_get_option(const mm_handle *h, const char *name) {
     if (strcmp(name, "tile_rows") == 0) return h->sg.tile_rows;
     if (strcmp(name, "blocks") == 0) return h->sg.nblocks;
     if (strcmp(name, "variant") == 0) return h->sg.variant;
+    if (strcmp(name, "rows_per_thread") == 0) return h->sg.march2 ? h->sg.rpt : 1;
+    if (strcmp(name, "march2") == 0) return h->sg.march2;
+    if (strcmp(name, "mass_uniform") == 0) return h->sg.mass_uniform;
+    if (strcmp(name, "tail") == 0) return sg_tail_ok(h) ? (h->sg.tail_in_kernel ? 2 : 1) : 0;
+    if (strcmp(name, "wrap_on_load") == 0) return h->sg.wrap_on_load;
     return -1;
 }
 

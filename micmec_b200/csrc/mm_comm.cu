@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "mm_internal.h"
+#include "mm_peer.cuh"
 #include "mm_reduce.cuh"
 
 namespace mm {
@@ -133,26 +134,6 @@ k_unpack(const __grid_constant__ PackArgs a, int64_t plane, int nzl, const doubl
 // doubles into all mailboxes, release-store the epoch, wait for all ranks' epochs and add the rows in rank order - every
 // rank gets bit-identical sums.  Epochs live in device memory (PeerCtl), so captured CUDA graphs replay correctly;
 // inboxes / mailboxes alternate by epoch parity: a rank can be at most one exchange ahead of a neighbour.
-struct PeerCtl {
-    unsigned long long halo_epoch, red_epoch;
-    unsigned int halo_done, pad;
-    unsigned long long fused_epoch;  // fused halo exchanges completed (k_halo_xy_fused)
-    unsigned int fused_done, pad2;
-};
-
-constexpr size_t kPeerFlagBytes = 1024;
-static size_t peer_mail_bytes(int P) { return sizeof(double) * 2 * P * 16; }
-static size_t peer_inbox_off(int P) { return kPeerFlagBytes + ((peer_mail_bytes(P) + 1023) & ~(size_t)1023); }
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 __global__ void __launch_bounds__(256)
 k_peer_push(const __grid_constant__ PackArgs a, int64_t plane, int nzl, char *up_base, char *down_base, size_t inbox_off,
             const PeerCtl *ctl) {

@@ -119,10 +119,19 @@ int sg_pos_from_aos(mm_handle *h, const double *d_aos);
 int sg_vel_from_aos(mm_handle *h, const double *d_aos);
 int sg_mass_from_aos(mm_handle *h, const double *d_masses);
 int sg_to_aos(mm_handle *h, int which, double *d_aos);
-int sg_force(mm_handle *h, bool write_g, int rot);
-int sg_step(mm_handle *h, bool write_g, int vm, bool lean);
+// what the tail of a k_march2 launch does after the reduction (mm_march2.cuh): OP_* bits of mm_scalar.cuh on the MD state
+struct SgTail {
+    unsigned ops;
+    void *state;
+};
+bool sg_tail_ok(const mm_handle *h);
+int sg_force(mm_handle *h, bool write_g, int rot, bool virial_only = false, const SgTail *tail = nullptr);
+int sg_step(mm_handle *h, bool write_g, int vm, bool lean, const SgTail *tail = nullptr);
 int sg_set_tile_rows(mm_handle *h, int rows);
 int sg_set_chunk(mm_handle *h, int chunk);
+int sg_set_rpt(mm_handle *h, int rpt);
+int sg_set_march2(mm_handle *h, int on);
+int sg_retile(mm_handle *h, int chunk_override);
 
 // ---- mm_comm.cu ---------------------------------------------------------------------------------------------
 int comm_halo(mm_handle *h, double **fields, int nfields, int npos);

@@ -26,6 +26,7 @@
 
 #include "mm_internal.h"
 #include "mm_march.cuh"
+#include "mm_march2.cuh"
 #include "mm_reduce.cuh"
 
 namespace mm {
@@ -130,6 +131,23 @@ k_halo_xy_fused(const __grid_constant__ HaloArgs h, int nx, int ny, int nxp, int
                 __threadfence();
             }
         }
+    }
+}
+
+// k_march2 takes the x / y images on load: after a launch that delivered its boundary planes to the neighbour slabs only
+// the hand-over remains (announce, wait for both neighbours' announcements) - unless the launch's tail already did it.
+__global__ void k_halo_handshake(const unsigned long long *flags, unsigned long long *epoch, unsigned long long *flag_lo,
+                                 unsigned long long *flag_hi) {
+    if (threadIdx.x == 0) {
+        const unsigned long long want = *epoch + 1;
+        __threadfence_system();
+        atomicAdd_system(flag_lo, 1ull);
+        atomicAdd_system(flag_hi, 1ull);
+        while (ld_acquire_sys_u64(flags) < want) {
+        }
+        while (ld_acquire_sys_u64(flags + 1) < want) {
+        }
+        *epoch = want;
     }
 }
 
@@ -316,7 +334,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int sg_encode_maps(mm_handle *h) {
+static int sg_encode_maps(mm_handle *h, int rows) {
     SGrid &g = h->sg;
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -330,7 +348,7 @@ static int sg_encode_maps(mm_handle *h) {
     }
     const cuuint64_t dims[3] = {(cuuint64_t)g.nxp, (cuuint64_t)(g.ny + 2), (cuuint64_t)(g.nzl + 3)};
     const cuuint64_t strides[2] = {(cuuint64_t)g.nxp * 8, (cuuint64_t)g.plane * 8};
-    const cuuint32_t box[3] = {(cuuint32_t)kBoxW, (cuuint32_t)g.tile_rows, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)kBoxW, (cuuint32_t)rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     auto one = [&](CUtensorMap *m, double *p) {
         return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -340,6 +358,15 @@ static int sg_encode_maps(mm_handle *h) {
     for (int c = 0; c < 2; c++)
         for (int d = 0; d < 3; d++) ok = ok && one(&g.tm_x[c][d], g.x[c][d]) && one(&g.tm_v[c][d], g.v[c][d]) && one(&g.tm_g[c][d], g.g[c][d]);
     ok = ok && one(&g.tm_m, g.m) && one(&g.tm_minv, g.minv);
+    // k_march2: image columns of the edge tiles (2 columns x rows, starting on an even column)
+    const cuuint32_t boxw[3] = {2, (cuuint32_t)rows, 1};
+    auto onew = [&](CUtensorMap *m, double *p) {
+        return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p, dims, strides, boxw, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    for (int c = 0; c < 2; c++)
+        for (int d = 0; d < 3; d++) ok = ok && onew(&g.tw_x[c][d], g.x[c][d]) && onew(&g.tw_v[c][d], g.v[c][d]) && onew(&g.tw_g[c][d], g.g[c][d]);
+    g.tma_rows = ok ? rows : 0;
     return ok ? MM_OK : MM_ERR_CUDA;
 }
 
@@ -350,11 +377,66 @@ bool sg_eligible(const mm_handle *h) {
     return h->structured && h->model == MM_MODEL_ORIGINAL && h->nx >= 2 && h->ny >= 2 && h->nz >= 2;
 }
 
+static int sg_tile_rows_total(const SGrid &g) { return g.march2 ? g.rpt * g.tile_rows : g.tile_rows; }
+
 int sg_blocks(const mm_handle *h, dim3 &grid) {
     const SGrid &g = h->sg;
-    const int ox = TX - 2, oy = g.tile_rows - 2;
+    const int ox = TX - 2, oy = sg_tile_rows_total(g) - 2;
     grid = dim3((g.nx + ox - 1) / ox, (g.ny + oy - 1) / oy, (g.nzl + g.chunk - 1) / g.chunk);
     return (int)(grid.x * grid.y * grid.z);
+}
+
+// Chunk length along z.  Every block marches chunk + 2 planes (one warm-up plane below, one plane above), one block per
+// SM: with T tiles and C = ceil(nzl / chunk) chunks the launch takes about ceil(T C / SMs) rounds of chunk + 2 plane
+// iterations.  Pick the chunk that minimises rounds * (chunk + 2); ties go to the longer chunk (fewer warm-up planes).
+static int sg_pick_chunk(const mm_handle *h) {
+    const SGrid &g = h->sg;
+    const int ox = TX - 2, oy = sg_tile_rows_total(g) - 2;
+    const int64_t tiles = (int64_t)((g.nx + ox - 1) / ox) * ((g.ny + oy - 1) / oy);
+    int best = g.nzl;
+    int64_t best_cost = -1;
+    for (int nchunks = 1; nchunks <= g.nzl; nchunks++) {
+        const int chunk = (g.nzl + nchunks - 1) / nchunks;
+        if (chunk < 4 && nchunks > 1) break;
+        if ((g.nzl + chunk - 1) / chunk != nchunks) continue;
+        const int64_t rounds = (tiles * nchunks + h->num_sms - 1) / h->num_sms;
+        const int64_t cost = rounds * (chunk + 2);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = chunk;
+        }
+    }
+    return best;
+}
+
+// (re)derive everything that depends on the tile shape: kernel family, tensor maps, chunk, number of block partials
+int sg_retile(mm_handle *h, int chunk_override) {
+    SGrid &g = h->sg;
+    const bool single = g.sp.ntypes == 1 && g.sp.nstates[0] == 1;
+    const bool want2 = g.march2_wanted && single && g.mass_uniform;
+    if (want2) {
+        g.march2 = 1;
+        if (g.tma_rows != g.rpt * g.tile_rows && sg_encode_maps(h, g.rpt * g.tile_rows) != MM_OK) g.march2 = 0;
+    } else {
+        g.march2 = 0;
+    }
+    if (!g.march2 && g.tma_rows != g.tile_rows) sg_encode_maps(h, g.tile_rows);
+    // Periodic images on load + tail launch (no ghost refresh, no hand-over kernel between two marching launches) pay off
+    // when slabs have to synchronise anyway; on one GPU the ghost-fill launch is cheaper than the image copies of the edge
+    // tiles (1.405 vs 1.447 ms per NPT step at 256^3, profiles/r02/g)
+    g.wrap_on_load = g.wrap_wanted >= 0 ? g.wrap_wanted : (h->slab_count > 1 ? 1 : 0);
+    g.tma_ok = g.tma_rows == sg_tile_rows_total(g) ? 1 : 0;
+    g.chunk = chunk_override > 0 ? chunk_override : sg_pick_chunk(h);
+    dim3 grid;
+    const int nb = sg_blocks(h, grid);
+    if (nb > g.nblocks_alloc) {
+        if (g.d_partials) cudaFree(g.d_partials);
+        g.d_partials = nullptr;
+        MM_CUDA(cudaMalloc(&g.d_partials, sizeof(double) * (size_t)nb * kRedSlots));
+        g.nblocks_alloc = nb;
+    }
+    g.nblocks = nb;
+    return MM_OK;
 }
 
 int sg_setup(mm_handle *h) {
@@ -393,19 +475,17 @@ int sg_setup(mm_handle *h) {
     }
     g.fused = (h->slab_count <= 1) ? 1 : 0;  // slabs switch it on once the peers are mapped (mm_comm.cu)
     MM_CUDA(cudaMalloc(&g.type, g.npad));
-    g.tma_ok = sg_encode_maps(h) == MM_OK ? 1 : 0;
-    MM_CUDA(cudaMalloc(&g.d_sc, sizeof(StepConsts)));
+    MM_CUDA(cudaMalloc(&g.d_sc, 512));  // StepConsts (248 B) + scratch doubles from byte 256 on (k_mass_range)
     MM_CUDA(cudaMalloc(&g.d_sp, sizeof(SParams)));
+    MM_CUDA(cudaMalloc(&g.d_tail_counter, 64));
+    MM_CUDA(cudaMemsetAsync(g.d_tail_counter, 0, 64, h->stream));
     MM_CUDA(cudaMemcpyAsync(g.d_sp, &g.sp, sizeof(SParams), cudaMemcpyHostToDevice, h->stream));
     MM_CUDA(cudaStreamSynchronize(h->stream));
     MM_CUDA(cudaHostAlloc(&g.h_sc, sizeof(StepConsts), cudaHostAllocDefault));
-    // chunk length along z: enough blocks for >= 4 waves of one block per SM, but no shorter than 8 planes
-    dim3 grid;
-    g.chunk = 32;
-    while (g.chunk > 8 && sg_blocks(h, grid) < 4 * h->num_sms) g.chunk /= 2;
-    g.nblocks = sg_blocks(h, grid);
-    g.nblocks_alloc = g.nblocks;
-    MM_CUDA(cudaMalloc(&g.d_partials, sizeof(double) * (size_t)g.nblocks * kRedSlots));
+    {
+        const int rc = sg_retile(h, 0);
+        if (rc != MM_OK) return rc;
+    }
     MM_CUDA(cudaMemsetAsync(g.type, 0, g.npad, h->stream));
     k_type_to_soa<<<grid_for(h, h->ncells, 256), 256, 0, h->stream>>>(h->d_cell_info, g.type, g.nx, g.ny, g.nzl, g.nxp);
     k_halo_xy_u8<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * g.nzl, 256), 256, 0, h->stream>>>(g.type, g.nx, g.ny, g.nxp, g.nzl);
@@ -423,6 +503,8 @@ void sg_free(mm_handle *h) {
     cudaFree(g.type);
     cudaFree(g.d_sc);
     cudaFree(g.d_sp);
+    cudaFree(g.d_tail_counter);
+    g.d_tail_counter = nullptr;
     cudaFree(g.d_partials);
     if (g.h_sc) cudaFreeHost(g.h_sc);
     g.active = 0;
@@ -457,6 +539,22 @@ int sg_halo(mm_handle *h, bool pos, bool vel, bool grad) {
         for (int d = 0; d < 3; d++) ha.f[ha.nfields++] = g.g[g.cg][d];
     if (ha.nfields == 0) return MM_OK;
     const int mask = (pos ? 1 : 0) | (vel ? 2 : 0) | (grad ? 4 : 0);
+    if (g.march2 && g.wrap_on_load) {  // x / y images are taken on load (mm_march2.cuh): only the z halo planes have to be current
+        const bool delivered = g.fused && g.fused_mask == mask;
+        g.fused_mask = 0;
+        if (delivered) {
+            if (h->slab_count > 1 && !g.tail_done) {
+                k_halo_handshake<<<1, 32, 0, h->stream>>>(g.halo_flags, g.halo_epoch, g.nb_flag[0], g.nb_flag[1]);
+                h->launches++;
+            }
+            g.tail_done = 0;
+            return MM_OK;
+        }
+        if (h->slab_count > 1) return comm_halo(h, ha.f, ha.nfields, ha.npos);
+        k_halo<<<grid_for(h, g.plane, 256), 256, 0, h->stream>>>(ha, g.plane, g.nzl, g.d_sc);
+        h->launches++;
+        return MM_OK;
+    }
     if (g.fused && g.fused_mask == mask) {  // the marching kernel delivered the boundary planes itself
         g.fused_mask = 0;
         k_halo_xy_fused<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * (g.nzl + 2), 256), 256, 0, h->stream>>>(
@@ -504,8 +602,48 @@ int sg_vel_from_aos(mm_handle *h, const double *d_aos) {
     return sg_halo(h, false, true, false);
 }
 
+// min / max of the node masses -> out[0], out[1] (one block; the masses are uploaded once per integrator)
+__global__ void __launch_bounds__(256) k_mass_range(const double *__restrict__ masses, int64_t n, double *out) {
+    __shared__ double lo[256], hi[256];
+    double a = masses[0], b = masses[0];
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        a = fmin(a, masses[i]);
+        b = fmax(b, masses[i]);
+    }
+    lo[threadIdx.x] = a;
+    hi[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            lo[threadIdx.x] = fmin(lo[threadIdx.x], lo[threadIdx.x + s]);
+            hi[threadIdx.x] = fmax(hi[threadIdx.x], hi[threadIdx.x + s]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = lo[0];
+        out[1] = hi[0];
+    }
+}
+
 int sg_mass_from_aos(mm_handle *h, const double *d_masses) {
     SGrid &g = h->sg;
+    {
+        // one node mass for the whole grid (micmec/utils.py:217 gives every node of a one-type grid the type mass): the
+        // fast path takes it as a kernel argument; anything else keeps the mass arrays and runs on k_march
+        double range[2] = {0.0, 0.0};
+        k_mass_range<<<1, 256, 0, h->stream>>>(d_masses, h->nnodes, reinterpret_cast<double *>(g.d_sc) + 32);
+        h->launches++;
+        MM_CUDA(cudaMemcpyAsync(range, reinterpret_cast<double *>(g.d_sc) + 32, sizeof(range), cudaMemcpyDeviceToHost, h->stream));
+        MM_CUDA(cudaStreamSynchronize(h->stream));
+        const int uniform = range[0] == range[1] ? 1 : 0;
+        g.mass = range[0];
+        if (uniform != g.mass_uniform) {
+            g.mass_uniform = uniform;
+            const int rc = sg_retile(h, 0);
+            if (rc != MM_OK) return rc;
+        }
+    }
     k_mass_to_soa<<<grid_for(h, h->nnodes, 256), 256, 0, h->stream>>>(d_masses, g.m, g.minv, g.nx, g.ny, g.nzl, g.nxp);
     h->launches++;
     return sg_halo_mass(h);
@@ -537,12 +675,56 @@ static void fill_args(mm_handle *h, MarchArgs &a) {
     a.m = g.m;
     a.minv = g.minv;
     a.type = g.type;
+    a.mass = g.mass;
     a.sc = g.d_sc;
     a.spg = g.d_sp;
     a.partials = g.d_partials;
     a.fused = 0;
     a.wrap_lo = a.wrap_hi = 0.0;
     for (int f = 0; f < 9; f++) a.halo_lo[f] = a.halo_hi[f] = nullptr;
+    memset(&a.tail, 0, sizeof(a.tail));
+}
+
+// The tail of a k_march2 launch can take over the reduction, the exchange between the slabs and the scalar algebra when
+// the boundary planes travel inside the marching kernel (one slab, or slabs in fused peer mode)
+bool sg_tail_ok(const mm_handle *h) {
+    const SGrid &g = h->sg;
+    if (!g.march2 || !g.tail_wanted || !g.fused || !g.wrap_on_load) return false;
+    return h->slab_count <= 1 || h->peer_mode != 0;
+}
+
+static void fill_tail(mm_handle *h, MarchArgs &a, const SgTail *tail) {
+    SGrid &g = h->sg;
+    if (!tail || !sg_tail_ok(h)) return;
+    a.tail.enabled = 1;
+    a.tail.ops = tail->ops;
+    a.tail.counter = g.d_tail_counter;
+    a.tail.state = tail->state;
+    a.tail.rvecs_dev = h->d_rvecs;
+    a.tail.sc_out = g.d_sc;
+    a.tail.n3 = 3.0 * (double)h->nnodes_global;
+    a.tail.nranks = h->slab_count > 1 ? h->slab_count : 1;
+    a.tail.rank = h->slab_rank;
+    a.tail.bases = h->slab_count > 1 ? h->d_peer_base : nullptr;
+    a.tail.ctl = h->d_peer_ctl;
+}
+
+// The same tail as ONE single-block launch behind the marching kernel (the default: measured against the in-kernel tail
+// in profiles/r02 - the last block of a marching launch runs the cold scalar code on an SM whose instruction caches hold the
+// plane loop, and every boundary block has to drain its peer stores before taking its ticket; as a separate launch the
+// tail costs one launch gap instead).  It replaces k_peer_allreduce + k_scalar + the halo hand-over of round 1.
+__global__ void __launch_bounds__(256) k_tail(const __grid_constant__ TailArgs t, const double *partials, const int nblocks) {
+    if (t.nranks > 1) __threadfence_system();  // stream order: the marching kernel's peer stores precede this launch
+    march_tail(t, partials, nblocks);
+}
+
+// run the tail of the marching launch that was just issued with `a` (in-kernel tails have already done it)
+static int finish_tail(mm_handle *h, MarchArgs &a) {
+    if (!a.tail.enabled || h->sg.tail_in_kernel) return MM_OK;
+    k_tail<<<1, 256, 0, h->stream>>>(a.tail, a.partials, h->sg.nblocks);
+    h->launches++;
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
 }
 
 // Fused halo: targets of the boundary planes of what a launch writes (array indices ax / av / ag inside the block)
@@ -613,37 +795,121 @@ static int launch_sel(mm_handle *h, const MarchArgs &a, bool step, int rot, int 
     return launch_one<0, SINGLE, 2, 0, false, VAR, TY>(h, a, write_g);
 }
 
-static int launch_march(mm_handle *h, const MarchArgs &a, bool step, int rot, int vm, bool lean, int write_g) {
-    const bool single = h->sg.sp.ntypes == 1 && h->sg.sp.nstates[0] == 1;
-    if (!single) return launch_sel<false, 0>(h, a, step, rot, vm, false, write_g);
-    const bool stageable = h->sg.tma_ok != 0;  // tensor maps encoded (sg_setup)
-    int var = h->sg.variant & 15;
-    if (!stageable) var &= ~2;
-    if (var & (2 | 8)) var &= ~1;  // the refill of a stage (and the one-barrier pipeline) rely on the block barrier
-    switch (var) {  // tuning variants kept for the measurements in profiles/ (bits: see k_march)
-        case 1: return launch_sel<true, 1>(h, a, step, rot, vm, lean, write_g);
-        case 2: return launch_sel<true, 2>(h, a, step, rot, vm, lean, write_g);
-        case 4: return launch_sel<true, 4>(h, a, step, rot, vm, lean, write_g);
-        case 5: return launch_sel<true, 5>(h, a, step, rot, vm, lean, write_g);
-        case 6: return launch_sel<true, 6>(h, a, step, rot, vm, lean, write_g);
-        case 8: return launch_sel<true, 8>(h, a, step, rot, vm, lean, write_g);
-        case 10: return launch_sel<true, 10>(h, a, step, rot, vm, lean, write_g);
-        case 14: return launch_sel<true, 14>(h, a, step, rot, vm, lean, write_g);
-        default: return launch_sel<true, 0>(h, a, step, rot, vm, lean, write_g);
+template <int MODE, int ROT, int VM, bool LEAN, int RPT, int TY, int PIN, bool WRAP, int UNR>
+static int launch_one2(mm_handle *h, const MarchArgs &a, int write_g) {
+    using Cfg = March2Cfg<RPT, TY>;
+    dim3 grid;
+    sg_blocks(h, grid);
+    prof_begin(h, MODE == M2_STEP ? 1 : 0);
+    constexpr size_t dyn = Cfg::dyn_bytes(MODE == M2_STEP ? 9 : 3);
+    static bool configured[64] = {false};
+    if (!configured[h->device & 63]) {
+        MM_CUDA(cudaFuncSetAttribute(k_march2<MODE, ROT, VM, LEAN, RPT, TY, PIN, WRAP, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        configured[h->device & 63] = true;
     }
+    TmaMaps maps;
+    const SGrid &g = h->sg;
+    for (int d = 0; d < 3; d++) {
+        maps.in[d] = g.tm_x[g.cx][d];
+        maps.in[3 + d] = g.tm_v[g.cv][d];
+        maps.in[6 + d] = g.tm_g[g.cg][d];
+    }
+    for (int d = 0; d < 3; d++) {
+        maps.xw[d] = g.tw_x[g.cx][d];
+        maps.xw[3 + d] = g.tw_v[g.cv][d];
+        maps.xw[6 + d] = g.tw_g[g.cg][d];
+    }
+    maps.in[9] = g.tm_m;
+    maps.in[10] = g.tm_minv;
+    k_march2<MODE, ROT, VM, LEAN, RPT, TY, PIN, WRAP, UNR><<<grid, dim3(TX, TY), dyn, h->stream>>>(g.sp.st[0], a, maps, write_g);
+    prof_end(h);
+    h->launches++;
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+
+// mode: M2_FORCE / M2_STEP / M2_VIRIAL (energy + virial only; rot 1)
+template <int RPT, int TY, int PIN, bool WRAP, int UNR>
+static int launch_sel2(mm_handle *h, const MarchArgs &a, int mode, int rot, int vm, bool lean, int write_g) {
+    if (mode == M2_STEP) {
+        if (lean) {
+            if (vm == 0) return launch_one2<M2_STEP, 0, 0, true, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+            return launch_one2<M2_STEP, 0, 1, true, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+        }
+        if (vm == 0) return launch_one2<M2_STEP, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+        if (vm == 1) return launch_one2<M2_STEP, 0, 1, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+        return launch_one2<M2_STEP, 0, 2, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+    }
+    if (mode == M2_VIRIAL) {
+        if (rot == 0) return launch_one2<M2_VIRIAL, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, 0);
+        return launch_one2<M2_VIRIAL, 1, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, 0);
+    }
+    if (rot == 0) return launch_one2<M2_FORCE, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+    if (rot == 1) return launch_one2<M2_FORCE, 1, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+    return launch_one2<M2_FORCE, 2, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+}
+
+#ifndef MM_MARCH2_CONFIGS  // (rows per thread, warps) pairs compiled into the library; the first one is the default
+#define MM_MARCH2_CONFIGS X(2, 8)
+#endif
+
+bool sg_march2_config_ok(int rpt, int ty) {
+#define X(R, T) if (rpt == R && ty == T) return true;
+    MM_MARCH2_CONFIGS
+#undef X
+    return false;
+}
+
+static int launch_march(mm_handle *h, const MarchArgs &a, int mode, int rot, int vm, bool lean, int write_g) {
+    const SGrid &g = h->sg;
+    if (g.march2) {
+        const int pin = mode == M2_STEP ? g.pin_step : g.pin_force;
+#define X(R, T)                                                                                   \
+    if (g.rpt == R && g.tile_rows == T) {                                                         \
+        if (!g.wrap_on_load) return launch_sel2<R, T, 0, false, 1>(h, a, mode, rot, vm, lean, write_g);               \
+        if (g.unroll == 2) {                                                                                          \
+            if (pin == 0) return launch_sel2<R, T, 0, true, 2>(h, a, mode, rot, vm, lean, write_g);                   \
+            return launch_sel2<R, T, 3, true, 2>(h, a, mode, rot, vm, lean, write_g);                                 \
+        }                                                                                                             \
+        if (pin == 0) return launch_sel2<R, T, 0, true, 1>(h, a, mode, rot, vm, lean, write_g);                       \
+        return launch_sel2<R, T, 3, true, 1>(h, a, mode, rot, vm, lean, write_g);                                     \
+    }
+        MM_MARCH2_CONFIGS
+#undef X
+        set_error("k_march2: tile configuration not compiled into this library");
+        return MM_ERR_INVALID;
+    }
+    const bool step = mode == M2_STEP;
+    const bool single = g.sp.ntypes == 1 && g.sp.nstates[0] == 1;
+    // general path: several cell types / metastable states / node masses (register-prefetch loads, mass arrays)
+    if (single) {
+#ifdef MM_KEEP_V14  // the round-1 kernel (TMA loads, one barrier per plane, two planes per trip): A/B builds only
+        if ((g.variant & 15) == 14 && g.tma_ok) return launch_sel<true, 14>(h, a, step, rot, vm, lean, write_g);
+#endif
+        return launch_sel<true, 0>(h, a, step, rot, vm, lean, write_g);
+    }
+    return launch_sel<false, 0>(h, a, step, rot, vm, false, write_g);
 }
 
 // Force evaluation at the stored positions.  rot: 0 = positions are true as stored, 1 = apply the pending rotation
 // Rpend on load, 2 = apply it and write the rotated positions to the other x set (which becomes current).
 // write_g: store the node gradient into the CURRENT g set (FORCE mode never reads g).
-int sg_force(mm_handle *h, bool write_g, int rot) {
+int sg_force(mm_handle *h, bool write_g, int rot, bool virial_only, const SgTail *tail) {
     SGrid &g = h->sg;
     MarchArgs a;
     fill_args(h, a);
+    fill_tail(h, a, tail);
     for (int d = 0; d < 3; d++) a.go[d] = g.g[g.cg][d];
     fill_fused(h, a, g.cx ^ 1, g.cv ^ 1, g.cg);
-    const int rc = launch_march(h, a, false, rot, 0, false, write_g ? 1 : 0);
+    // virial_only: energy and virial of a geometry whose gradient nobody reads (k_march2 skips the gather; k_march
+    // computes it anyway and drops it)
+    const int mode = (virial_only && !write_g && rot != 2 && g.march2) ? M2_VIRIAL : M2_FORCE;
+    MarchArgs ak = a;
+    if (!g.tail_in_kernel) ak.tail.enabled = 0;
+    int rc = launch_march(h, ak, mode, rot, 0, false, write_g ? 1 : 0);
+    if (rc == MM_OK) rc = finish_tail(h, a);
     g.fused_mask = g.fused ? ((rot == 2 ? 1 : 0) | (write_g ? 4 : 0)) : 0;
+    g.tail_done = a.tail.enabled;
     if (rot == 2) g.cx ^= 1;
     return rc;
 }
@@ -651,38 +917,48 @@ int sg_force(mm_handle *h, bool write_g, int rot) {
 // Fused kick-drift-force-kick.  Reads the current x, v, g sets, writes the other x and v sets (and g when write_g)
 // and flips them.  vm: pending velocity transform 0 none / 1 scalar / 2 matrix.  The halo planes of what was
 // written are refreshed afterwards by the caller (sg_halo).
-int sg_step(mm_handle *h, bool write_g, int vm, bool lean) {
+int sg_step(mm_handle *h, bool write_g, int vm, bool lean, const SgTail *tail) {
     SGrid &g = h->sg;
     MarchArgs a;
     fill_args(h, a);
+    fill_tail(h, a, tail);
     fill_fused(h, a, g.cx ^ 1, g.cv ^ 1, g.cg ^ 1);
-    const int rc = launch_march(h, a, true, 0, vm, lean && vm != 2, write_g ? 1 : 0);
+    MarchArgs ak = a;
+    if (!g.tail_in_kernel) ak.tail.enabled = 0;
+    int rc = launch_march(h, ak, M2_STEP, 0, vm, lean && vm != 2, write_g ? 1 : 0);
+    if (rc == MM_OK) rc = finish_tail(h, a);
     g.fused_mask = g.fused ? (3 | (write_g ? 4 : 0)) : 0;
+    g.tail_done = a.tail.enabled;
     g.cx ^= 1;
     g.cv ^= 1;
     if (write_g) g.cg ^= 1;
     return rc;
 }
 
-int sg_set_chunk(mm_handle *h, int chunk) {  // tuning: planes per block along z
-    if (chunk < 1) return MM_ERR_INVALID;
-    h->sg.chunk = chunk;
-    return sg_set_tile_rows(h, h->sg.tile_rows);
+int sg_set_chunk(mm_handle *h, int chunk) {  // tuning: planes per block along z (0 = cost model)
+    if (chunk < 0) return MM_ERR_INVALID;
+    return sg_retile(h, chunk);
 }
 
-int sg_set_tile_rows(mm_handle *h, int rows) {
+int sg_set_tile_rows(mm_handle *h, int rows) {  // warps per block
     SGrid &g = h->sg;
-    if (rows != 8) return MM_ERR_INVALID;
+    if (!(rows == 8 || (g.march2_wanted && sg_march2_config_ok(g.rpt, rows)))) return MM_ERR_INVALID;
     g.tile_rows = rows;
-    dim3 grid;
-    const int nb = sg_blocks(h, grid);
-    if (nb > g.nblocks_alloc) {
-        cudaFree(g.d_partials);
-        MM_CUDA(cudaMalloc(&g.d_partials, sizeof(double) * (size_t)nb * kRedSlots));
-        g.nblocks_alloc = nb;
-    }
-    g.nblocks = nb;
-    return MM_OK;
+    return sg_retile(h, 0);
+}
+
+int sg_set_rpt(mm_handle *h, int rpt) {  // node rows per thread of k_march2
+    SGrid &g = h->sg;
+    if (!sg_march2_config_ok(rpt, g.tile_rows)) return MM_ERR_INVALID;
+    g.rpt = rpt;
+    return sg_retile(h, 0);
+}
+
+int sg_set_march2(mm_handle *h, int on) {
+    SGrid &g = h->sg;
+    g.march2_wanted = on ? 1 : 0;
+    if (!on) g.tile_rows = 8;
+    return sg_retile(h, 0);
 }
 
 }  // namespace mm

@@ -61,6 +61,8 @@ struct SGrid {
     uint8_t *type = nullptr;
     int cx = 0, cv = 0, cg = 0;     // which copy is current
     CUtensorMap tm_x[2][3], tm_v[2][3], tm_g[2][3], tm_m, tm_minv;  // load descriptors of the arrays above
+    CUtensorMap tw_x[2][3], tw_v[2][3], tw_g[2][3];                 // ... with the 2-column box of k_march2's image columns
+    unsigned int *d_tail_counter = nullptr;                         // k_march2 tail: blocks finished
     int tma_ok = 0;                 // descriptors encoded (driver entry point available, pitch constraints met)
     // fused halo (see MarchArgs): where the z neighbours' copies of this slab's arrays live (own block when there is one
     // slab), their plane counts, and what the last marching launch already delivered
@@ -73,12 +75,27 @@ struct SGrid {
     unsigned int *halo_done = nullptr;         // its block counter
     int fused = 0;                  // k_march also writes the boundary planes into the neighbours' halo planes
     int fused_mask = 0;             // fields delivered by the last launch: 1 positions, 2 velocities, 4 gradients
+    int tail_done = 0;              // ... and its tail already exchanged with the other slabs (k_march2)
     StepConsts *d_sc = nullptr;
     SParams *d_sp = nullptr;        // device copy of sp
     StepConsts *h_sc = nullptr;     // pinned staging
     double *d_partials = nullptr;   // [nblocks][kRedSlots]
     int nblocks = 0, nblocks_alloc = 0;
     int tile_rows = 8;              // TY of the marching kernel (warps per block)
+    // fast path (mm_march2.cuh): one type, one state, uniform node mass, tensor maps available
+    int march2 = 0;                 // the handle's launches go to k_march2
+    int march2_wanted = 1;          // option "march2": 0 keeps everything on k_march
+    int unroll = 1;                 // planes per trip of k_march2's steady loop (1 / 2)
+    int wrap_on_load = -1;          // k_march2 takes the x / y periodic images on load instead of from ghost nodes; -1 = decide
+                                    // from the decomposition (sg_retile: slabs yes, a single GPU no - measured in profiles/r02)
+    int wrap_wanted = -1;           // option "wrap_on_load"
+    int tail_in_kernel = 0;         // the tail runs inside the marching launch (last block) instead of as its own launch
+    int tail_wanted = 1;            // option "tail": 0 keeps the reduction / exchange / scalar algebra in their own launches
+    int rpt = 2;                    // node rows per thread of k_march2 (tile = 32 x rpt * tile_rows nodes)
+    int pin_step = 0, pin_force = 3;  // rows of Bq held in per-thread registers (k_march2 PIN) by the STEP / FORCE launches
+    int tma_rows = 0;               // box rows the tensor maps were encoded for
+    int mass_uniform = 1;           // all node masses equal (checked when the masses are uploaded)
+    double mass = 1.0;
     int variant = 14;               // tuning bits of the marching kernel (k_march VAR); default: TMA loads, one barrier
                                     // per plane, two planes per loop trip
     int chunk = 32;                 // owned planes per block along z
@@ -89,6 +106,24 @@ struct SGrid {
 // a padded plane; coordinates outside the array read as zero (the partial tiles at the upper x / y edge)
 struct alignas(64) TmaMaps {
     CUtensorMap in[11];  // x0 x1 x2 v0 v1 v2 g0 g1 g2 m 1/m
+    CUtensorMap xw[9];   // k_march2: the same nine arrays with a box of 2 x rows nodes (the periodic image column of an edge tile)
+};
+
+// Tail of a k_march2 launch: the last block to finish sums the block partials in a fixed order, exchanges the 16 sums with
+// the other z-slabs through the peer mailboxes (mm_comm.cu; the exchange also tells every rank that its neighbours'
+// boundary planes have landed) and runs the thermostat / barostat algebra (mm_scalar.cuh) - what used to be the
+// k_peer_allreduce, k_scalar and k_halo_xy_fused launches between two marching kernels.
+struct TailArgs {
+    int enabled;
+    unsigned ops;            // OP_* bits of mm_scalar.cuh
+    unsigned int *counter;   // blocks finished (zeroed by the tail)
+    void *state;             // MDState*
+    double *rvecs_dev;       // the handle's device copy of the domain vectors (the barostat updates it)
+    StepConsts *sc_out;
+    double n3;               // 3 x global number of nodes
+    int nranks, rank;
+    char *const *bases;      // peer control blocks of all slabs (null for one slab)
+    void *ctl;               // PeerCtl*
 };
 
 struct MarchArgs {
@@ -111,6 +146,8 @@ struct MarchArgs {
     double *halo_hi[9];   // own plane nzl -> plane 0 of the neighbour above
     double wrap_lo, wrap_hi;
     int fused;
+    double mass;  // k_march2: the uniform node mass
+    TailArgs tail;
     const StepConsts *sc;
     const SParams *spg;  // the constants once more in global memory (pinned register copies are loaded from here)
     double *partials;
