@@ -167,8 +167,8 @@ int mm_create(const mm_desc *desc, mm_handle **out) {
             return invalid("mm_create: a periodic axis needs at least 2 cells (1-wide axes are degenerate in the reference)");
         if (desc->slab_count > 1 && (desc->slab_rank < 0 || desc->slab_rank >= desc->slab_count))
             return invalid("mm_create: slab_rank out of range");
-        if (desc->slab_count > 1 && desc->model != MM_MODEL_ORIGINAL)
-            return invalid("mm_create: the slab decomposition runs on the structured-grid kernels (model 'original')");
+        if (desc->slab_count > 1 && desc->model != MM_MODEL_ORIGINAL && (desc->ntypes != 1 || !desc->type_nstates || desc->type_nstates[0] != 1))
+            return invalid("mm_create: the slab decomposition runs on the structured-grid kernels ('default' model: one cell type with one state)");
     } else if (desc->slab_count > 1) {
         return invalid("mm_create: the slab decomposition needs a structured grid (nx, ny, nz)");
     } else if (!desc->surrounding_nodes || !desc->surrounding_cells || !desc->shift) {

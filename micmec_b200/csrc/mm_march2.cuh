@@ -156,7 +156,7 @@ static __device__ __noinline__ void march_tail(const TailArgs &t, const double *
         reinterpret_cast<double *>(t.state)[i] = reinterpret_cast<const double *>(&sm_state)[i];
 }
 
-template <int MODE, int ROT, int VM, bool LEAN, int RPT, int TY, int PIN, bool WRAP, int UNR>
+template <int MODEL, int MODE, int ROT, int VM, bool LEAN, int RPT, int TY, int PIN, bool WRAP, int UNR>
 __global__ void __launch_bounds__(TX *TY, 1)
 k_march2(const __grid_constant__ SState Pc, const __grid_constant__ MarchArgs a, const __grid_constant__ TmaMaps maps,
          const int write_g) {
@@ -246,8 +246,21 @@ k_march2(const __grid_constant__ SState Pc, const __grid_constant__ MarchArgs a,
     }
 
     // carried from plane to plane, per row
-    double fpxy[RPT][3], fdxy[RPT][3], fpyd[RPT][3];  // forward: xy-combined sums / differences of the previous plane
-    double Dp[RPT][9];                                // D' of the previous cell layer
+    // `original` model (separable stencils): forward xy-combined sums / differences of the previous plane, D' of the previous
+    // cell layer.  `default` model (eight corner matrices, nanocell.py:63-132): the four in-plane vertices of the previous
+    // plane (00, 10, 01, 11) and the gradients of the previous layer's upper (dz = 1) vertices.
+    constexpr bool DEF = MODEL == MM_MODEL_DEFAULT;
+    double fpxy[RPT][3], fdxy[RPT][3], fpyd[RPT][3];
+    double Dp[RPT][9];
+    double rp[DEF ? RPT : 1][4][3], Gp[DEF ? RPT : 1][4][3];
+    if (DEF) {
+#pragma unroll
+        for (int r = 0; r < RPT; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) rp[r][c][j] = Gp[r][c][j] = 0.0;
+    }
     double vh[RPT][3];                                // STEP: half-kicked velocity of the previous plane
     double vh2[3] = {0, 0, 0}, gdc[3] = {0, 0, 0};    // row 0: ... of the plane before that / its own-row gradient part
 #pragma unroll
@@ -396,11 +409,19 @@ k_march2(const __grid_constant__ SState Pc, const __grid_constant__ MarchArgs a,
         __syncthreads();
         if (p + NST <= c1) stage_issue(p + NST, st);  // all threads have read stage st
         double pxy[RPT][3], dxy[RPT][3], pyd[RPT][3];
+        double cur[DEF ? RPT : 1][4][3];  // default model: the four in-plane vertices of this plane
 #pragma unroll
         for (int q = 0; q < RPT; q++) {
 #pragma unroll
             for (int j = 0; j < 3; j++) {
                 const double rn = (q + 1 < RPT) ? r[(q + 1 < RPT) ? q + 1 : q][j] : sf[par][j][wp][lane];
+                if (DEF) {
+                    cur[q][0][j] = r[q][j];
+                    cur[q][2][j] = rn;
+                    cur[q][1][j] = __shfl_down_sync(0xffffffffu, r[q][j], 1);
+                    cur[q][3][j] = __shfl_down_sync(0xffffffffu, rn, 1);
+                    continue;
+                }
                 const double py = rn + r[q][j], dy = rn - r[q][j];
                 const double pyn = __shfl_down_sync(0xffffffffu, py, 1);
                 const double dyn = __shfl_down_sync(0xffffffffu, dy, 1);
@@ -420,6 +441,121 @@ k_march2(const __grid_constant__ SState Pc, const __grid_constant__ MarchArgs a,
         double yp_prev[3] = {0, 0, 0};  // (ya + yb) of the row below inside this thread
 #pragma unroll
         for (int q = 0; q < RPT; q++) {
+            if (DEF) {
+                // ---- `default` model: eight corner evaluations per cell (nanocell.py:63-132) --------------
+                // vertex (dx, dy, dz): dz = 0 -> rp[dx + 2 dy] (plane p-1), dz = 1 -> cur[dx + 2 dy] (plane p).  Corner a uses the
+                // three cell edges that meet in it, oriented +axis.  Constants are those of the metric form with Hs = H
+                // (fold_sparams: Bq x 32, c0 / 16 with respect to the averaged model).
+                double Gv[8][3];  // gradient of vertex dx + 2 dy + 4 dz
+                if (CELL) {
+#pragma unroll
+                    for (int v = 0; v < 8; v++)
+#pragma unroll
+                        for (int j = 0; j < 3; j++) Gv[v][j] = 0.0;
+                    double esum = 0.0, vsum[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+                    for (int ca = 0; ca < 8; ca++) {
+                        const int ax = ca & 1, ay = (ca >> 1) & 1, az = ca >> 2;
+                        // vertex position by (dx, dy, dz)
+                        auto V = [&](int dx, int dy, int dz, int j) -> double { return dz ? cur[q][dx + 2 * dy][j] : rp[q][dx + 2 * dy][j]; };
+                        double Hs[9];
+#pragma unroll
+                        for (int j = 0; j < 3; j++) {
+                            Hs[j] = V(1, ay, az, j) - V(0, ay, az, j);
+                            Hs[3 + j] = V(ax, 1, az, j) - V(ax, 0, az, j);
+                            Hs[6 + j] = V(ax, ay, 1, j) - V(ax, ay, 0, j);
+                        }
+                        double d[6], Sq[6], D[9];
+                        d[0] = fma(Hs[2], Hs[2], fma(Hs[1], Hs[1], fma(Hs[0], Hs[0], -Pc.c0[0])));
+                        d[1] = fma(Hs[5], Hs[5], fma(Hs[4], Hs[4], fma(Hs[3], Hs[3], -Pc.c0[1])));
+                        d[2] = fma(Hs[8], Hs[8], fma(Hs[7], Hs[7], fma(Hs[6], Hs[6], -Pc.c0[2])));
+                        d[3] = fma(Hs[5], Hs[8], fma(Hs[4], Hs[7], fma(Hs[3], Hs[6], -Pc.c0[3])));
+                        d[4] = fma(Hs[2], Hs[8], fma(Hs[1], Hs[7], fma(Hs[0], Hs[6], -Pc.c0[4])));
+                        d[5] = fma(Hs[2], Hs[5], fma(Hs[1], Hs[4], fma(Hs[0], Hs[3], -Pc.c0[5])));
+#pragma unroll
+                        for (int I = 0; I < 6; I++) {
+                            const double *B = Pc.Bq + I * 6;
+                            const double lo = fma(B[2], d[2], fma(B[1], d[1], B[0] * d[0]));
+                            Sq[I] = fma(B[5], d[5], fma(B[4], d[4], fma(B[3], d[3], lo)));
+                        }
+                        esum += 0.25 * fma(2.0, fma(d[5], Sq[5], fma(d[4], Sq[4], d[3] * Sq[3])), fma(d[2], Sq[2], fma(d[1], Sq[1], d[0] * Sq[0])));
+#pragma unroll
+                        for (int j = 0; j < 3; j++) {  // D_a = Sq H_a (= 1/8 V0 h0^-T sym(sigma_a) G_a, nanocell.py:108-130)
+                            D[j] = fma(Sq[4], Hs[6 + j], fma(Sq[5], Hs[3 + j], Sq[0] * Hs[j]));
+                            D[3 + j] = fma(Sq[3], Hs[6 + j], fma(Sq[1], Hs[3 + j], Sq[5] * Hs[j]));
+                            D[6 + j] = fma(Sq[2], Hs[6 + j], fma(Sq[3], Hs[3 + j], Sq[4] * Hs[j]));
+                        }
+                        if (!VIRIAL) {
+#pragma unroll
+                            for (int j = 0; j < 3; j++) {  // the edge's upper end gains D_a[i], its lower end loses it
+                                Gv[1 + 2 * ay + 4 * az][j] += D[j];
+                                Gv[0 + 2 * ay + 4 * az][j] -= D[j];
+                                Gv[ax + 2 + 4 * az][j] += D[3 + j];
+                                Gv[ax + 0 + 4 * az][j] -= D[3 + j];
+                                Gv[ax + 2 * ay + 4][j] += D[6 + j];
+                                Gv[ax + 2 * ay + 0][j] -= D[6 + j];
+                            }
+                        }
+                        if (WANT_VIR && decltype(node_tag)::value) {  // sum_a D_a^T H_a
+                            vsum[0] += fma(D[6], Hs[6], fma(D[3], Hs[3], D[0] * Hs[0]));
+                            vsum[1] += fma(D[7], Hs[7], fma(D[4], Hs[4], D[1] * Hs[1]));
+                            vsum[2] += fma(D[8], Hs[8], fma(D[5], Hs[5], D[2] * Hs[2]));
+                            vsum[3] += fma(D[7], Hs[8], fma(D[4], Hs[5], D[1] * Hs[2]));
+                            vsum[4] += fma(D[6], Hs[8], fma(D[3], Hs[5], D[0] * Hs[2]));
+                            vsum[5] += fma(D[6], Hs[7], fma(D[3], Hs[4], D[0] * Hs[1]));
+                        }
+                    }
+                    if (decltype(node_tag)::value) {  // the warm-up layer c0-1 belongs to the chunk below
+                        acc[0] = fma(ownf[q], esum, acc[0]);
+                        if (WANT_VIR) {
+#pragma unroll
+                            for (int u = 0; u < 6; u++) acc[1 + u] = fma(ownf[q], vsum[u], acc[1 + u]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) rp[q][c][j] = cur[q][c][j];
+                // backward: node (lane, row, p-1) gathers vertex (dx, dy, dz) of cell (lane - dx, row - dy, layer p-1-dz):
+                // z in registers (Gp), x by shuffle, y in registers / through shared memory
+                if (NODE) {
+                    double gd[3], yp[3];
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const double z00 = Gp[q][0][j] + Gv[0][j], z10 = Gp[q][1][j] + Gv[1][j];
+                        const double z01 = Gp[q][2][j] + Gv[2][j], z11 = Gp[q][3][j] + Gv[3][j];
+                        gd[j] = z00 + __shfl_up_sync(0xffffffffu, z10, 1);  // cells of this row (dy = 0)
+                        yp[j] = z01 + __shfl_up_sync(0xffffffffu, z11, 1);  // what the row above gathers (dy = 1)
+                    }
+                    if (q == 0) {
+#pragma unroll
+                        for (int j = 0; j < 3; j++) {
+                            gdc[j] = gd[j];
+                            vh2[j] = vh[0][j];
+                        }
+                    } else {
+                        finish_node(halo_tag, own[q], ownf[q], idx - plane + q * nxp, p - 1, yp_prev, gd, vh[q]);
+                    }
+                    if (q == RPT - 1) {
+#pragma unroll
+                        for (int j = 0; j < 3; j++) sb[par][j][w][lane] = yp[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; j++) yp_prev[j] = yp[j];
+                }
+                if (CELL && !VIRIAL) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+#pragma unroll
+                        for (int j = 0; j < 3; j++) Gp[q][c][j] = Gv[4 + c][j];
+                }
+                if (STEP) {
+#pragma unroll
+                    for (int j = 0; j < 3; j++) vh[q][j] = vcur[q][j];
+                }
+                continue;
+            }
             double D[9];
             if (CELL) {
                 double Hs[9];

@@ -67,7 +67,11 @@ enum : unsigned {
 
 // ------------------------------------------------------------------------------------------- 3x3 helpers ----
 static __device__ __forceinline__ void mat_mul(const double *a, const double *b, double *c) {  // c = a b (c may alias neither)
+    // unrolled: nine independent chains of three - this code runs on ONE thread between two marching launches, its
+    // latency is on the critical path of every step
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) c[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
 }
 
@@ -97,9 +101,11 @@ static __device__ void sym_expm(const double *a_in, double scale, double *out) {
                 term[i] = X[i];
                 sum[i] = ((i % 4 == 0) ? 1.0 : 0.0) + X[i];
             }
+#pragma unroll
             for (int k = 2; k <= 9; k++) {
                 mat_mul(term, X, t);
-                const double inv = 1.0 / (double)k;
+                const double inv = 1.0 / (double)k;  // compile-time constant once unrolled
+#pragma unroll
                 for (int i = 0; i < 9; i++) {
                     term[i] = t[i] * inv;
                     sum[i] += term[i];
@@ -208,7 +214,8 @@ static __device__ void update_baro_vel(MDState &s) {
     for (int i = 0; i < 6; i++) pv[i] = s.mvv[i] - s.vir[i];  // both symmetric here: 0.5 (pv^T + pv) is a no-op
     sym6_to_full(pv, G);
     const double iso = 2.0 * s.ekin / s.ndof - s.b_press * volume_of(s.rvecs);
-    for (int i = 0; i < 9; i++) G[i] = (G[i] + ((i % 4 == 0) ? iso : 0.0)) / s.mass_press;
+#pragma unroll
+    for (int i = 0; i < 9; i++) G[i] = (G[i] + ((i % 4 == 0) ? iso : 0.0)) / s.mass_press;  // nine independent divisions
     if (!s.aniso) {
         s.vp[0] += (G[0] + G[4] + G[8]) * s.timestep / 4.0;
     } else {
@@ -310,6 +317,7 @@ static __device__ void properties(MDState &s, double n3) {  // verlet.py:171-190
     sym6_to_full(s.mvv, m);
     sym6_to_full(s.vir, v);
     if (s.volume > 0.0) {  // verlet.py:185: only for periodic systems
+#pragma unroll
         for (int i = 0; i < 9; i++) s.ptens[i] = (m[i] - v[i]) / s.volume;
         s.press = (s.ptens[0] + s.ptens[4] + s.ptens[8]) / 3.0;
     }

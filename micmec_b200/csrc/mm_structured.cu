@@ -263,7 +263,10 @@ k_type_to_soa(const uint8_t *__restrict__ info, uint8_t *type, int nx, int ny, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-static void fold_sparams(const KParams &kp, SParams &sp) {
+// model: the averaged `original` cell works on Hs = 4 H (what the separable stencil produces), the eight-corner `default`
+// cell on Hs = H_a with weight 1/8: Bq = w V0 / (2 alpha^4) K' A K and c0 = alpha^2 h0 h0^T with (alpha, w) = (4, 1) / (1, 1/8)
+static void fold_sparams(const KParams &kp, SParams &sp, int model) {
+    const long double bq_div = model == MM_MODEL_DEFAULT ? 16.0L : 512.0L, c0_mul = model == MM_MODEL_DEFAULT ? 1.0L : 16.0L;
     sp.ntypes = kp.ntypes;
     for (int t = 0; t < MM_MAX_TYPES; t++) {
         sp.nstates[t] = kp.nstates[t];
@@ -302,7 +305,7 @@ static void fold_sparams(const KParams &kp, SParams &sp) {
                 long double acc = 0.0L;
                 for (int M = 0; M < 6; M++) acc += Kp[I][M] * AK[M][J];
                 // eps = 1/2 K (c - c0), c = Hs Hs^T / 16, Sq = V0/16 hi^T s hi  ->  1/2 * 1/16 * 1/16
-                S.Bq[I * 6 + J] = (double)(acc * (long double)P.v0 / 512.0L);
+                S.Bq[I * 6 + J] = (double)(acc * (long double)P.v0 / bq_div);
             }
         // c0 = h0 h0^T; h0 itself is not kept in StateP: invert hi (3x3 adjugate)
         const double *m = P.hi;
@@ -323,7 +326,7 @@ static void fold_sparams(const KParams &kp, SParams &sp) {
             const int a = vi[I], b = vj[I];
             long double acc = 0.0L;
             for (int j = 0; j < 3; j++) acc += h0[a * 3 + j] * h0[b * 3 + j];
-            S.c0[I] = (double)(16.0L * acc);
+            S.c0[I] = (double)(c0_mul * acc);
         }
     }
 }
@@ -374,7 +377,9 @@ static int sg_encode_maps(mm_handle *h, int rows) {
 static inline int sg_array(int quantity, int c, int d) { return (quantity * 2 + c) * 3 + d; }
 
 bool sg_eligible(const mm_handle *h) {
-    return h->structured && h->model == MM_MODEL_ORIGINAL && h->nx >= 2 && h->ny >= 2 && h->nz >= 2;
+    if (!h->structured || h->nx < 2 || h->ny < 2 || h->nz < 2) return false;
+    // the `default` (eight-corner) model exists on k_march2 only: one cell type with one metastable state
+    return h->model == MM_MODEL_ORIGINAL || (h->kp.ntypes == 1 && h->kp.nstates[0] == 1);
 }
 
 static int sg_tile_rows_total(const SGrid &g) { return g.march2 ? g.rpt * g.tile_rows : g.tile_rows; }
@@ -450,7 +455,11 @@ int sg_setup(mm_handle *h) {
     g.nxp = (g.nx + kGhostX + 1 + 1) & ~1;  // ghost nodes on both sides (mm_structured.cuh), even pitch: 16-byte rows for TMA
     g.plane = (int64_t)g.nxp * (g.ny + 2);
     g.npad = g.plane * (g.nzl + 3);  // two halo planes + one spare plane for the prefetch of the marching kernel
-    fold_sparams(h->kp, g.sp);
+    fold_sparams(h->kp, g.sp, h->model);
+    if (h->model == MM_MODEL_DEFAULT) {  // the eight-corner cell keeps one node row per thread (register budget)
+        g.rpt = 1;
+        g.tile_rows = 8;
+    }
     // all node arrays in one allocation: array a at block + a * stride (order: sg_array)
     // (the stride is skewed by an odd number of 256-byte lines: with a power-of-two-ish stride the same node of all 20
     // arrays falls on the same memory channel and the 20 streams of the marching kernel queue up there)
@@ -795,7 +804,7 @@ static int launch_sel(mm_handle *h, const MarchArgs &a, bool step, int rot, int 
     return launch_one<0, SINGLE, 2, 0, false, VAR, TY>(h, a, write_g);
 }
 
-template <int MODE, int ROT, int VM, bool LEAN, int RPT, int TY, int PIN, bool WRAP, int UNR>
+template <int MODEL, int MODE, int ROT, int VM, bool LEAN, int RPT, int TY, int PIN, bool WRAP, int UNR>
 static int launch_one2(mm_handle *h, const MarchArgs &a, int write_g) {
     using Cfg = March2Cfg<RPT, TY>;
     dim3 grid;
@@ -804,7 +813,7 @@ static int launch_one2(mm_handle *h, const MarchArgs &a, int write_g) {
     constexpr size_t dyn = Cfg::dyn_bytes(MODE == M2_STEP ? 9 : 3);
     static bool configured[64] = {false};
     if (!configured[h->device & 63]) {
-        MM_CUDA(cudaFuncSetAttribute(k_march2<MODE, ROT, VM, LEAN, RPT, TY, PIN, WRAP, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        MM_CUDA(cudaFuncSetAttribute(k_march2<MODEL, MODE, ROT, VM, LEAN, RPT, TY, PIN, WRAP, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         configured[h->device & 63] = true;
     }
     TmaMaps maps;
@@ -821,7 +830,7 @@ static int launch_one2(mm_handle *h, const MarchArgs &a, int write_g) {
     }
     maps.in[9] = g.tm_m;
     maps.in[10] = g.tm_minv;
-    k_march2<MODE, ROT, VM, LEAN, RPT, TY, PIN, WRAP, UNR><<<grid, dim3(TX, TY), dyn, h->stream>>>(g.sp.st[0], a, maps, write_g);
+    k_march2<MODEL, MODE, ROT, VM, LEAN, RPT, TY, PIN, WRAP, UNR><<<grid, dim3(TX, TY), dyn, h->stream>>>(g.sp.st[0], a, maps, write_g);
     prof_end(h);
     h->launches++;
     MM_CUDA(cudaGetLastError());
@@ -829,24 +838,24 @@ static int launch_one2(mm_handle *h, const MarchArgs &a, int write_g) {
 }
 
 // mode: M2_FORCE / M2_STEP / M2_VIRIAL (energy + virial only; rot 1)
-template <int RPT, int TY, int PIN, bool WRAP, int UNR>
+template <int MODEL, int RPT, int TY, int PIN, bool WRAP, int UNR>
 static int launch_sel2(mm_handle *h, const MarchArgs &a, int mode, int rot, int vm, bool lean, int write_g) {
     if (mode == M2_STEP) {
         if (lean) {
-            if (vm == 0) return launch_one2<M2_STEP, 0, 0, true, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
-            return launch_one2<M2_STEP, 0, 1, true, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+            if (vm == 0) return launch_one2<MODEL, M2_STEP, 0, 0, true, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+            return launch_one2<MODEL, M2_STEP, 0, 1, true, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
         }
-        if (vm == 0) return launch_one2<M2_STEP, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
-        if (vm == 1) return launch_one2<M2_STEP, 0, 1, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
-        return launch_one2<M2_STEP, 0, 2, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+        if (vm == 0) return launch_one2<MODEL, M2_STEP, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+        if (vm == 1) return launch_one2<MODEL, M2_STEP, 0, 1, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+        return launch_one2<MODEL, M2_STEP, 0, 2, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
     }
     if (mode == M2_VIRIAL) {
-        if (rot == 0) return launch_one2<M2_VIRIAL, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, 0);
-        return launch_one2<M2_VIRIAL, 1, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, 0);
+        if (rot == 0) return launch_one2<MODEL, M2_VIRIAL, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, 0);
+        return launch_one2<MODEL, M2_VIRIAL, 1, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, 0);
     }
-    if (rot == 0) return launch_one2<M2_FORCE, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
-    if (rot == 1) return launch_one2<M2_FORCE, 1, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
-    return launch_one2<M2_FORCE, 2, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+    if (rot == 0) return launch_one2<MODEL, M2_FORCE, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+    if (rot == 1) return launch_one2<MODEL, M2_FORCE, 1, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+    return launch_one2<MODEL, M2_FORCE, 2, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
 }
 
 #ifndef MM_MARCH2_CONFIGS  // (rows per thread, warps) pairs compiled into the library; the first one is the default
@@ -854,6 +863,7 @@ static int launch_sel2(mm_handle *h, const MarchArgs &a, int mode, int rot, int 
 #endif
 
 bool sg_march2_config_ok(int rpt, int ty) {
+    if (rpt == 1 && ty == 8) return true;  // the default-model instantiation
 #define X(R, T) if (rpt == R && ty == T) return true;
     MM_MARCH2_CONFIGS
 #undef X
@@ -862,17 +872,25 @@ bool sg_march2_config_ok(int rpt, int ty) {
 
 static int launch_march(mm_handle *h, const MarchArgs &a, int mode, int rot, int vm, bool lean, int write_g) {
     const SGrid &g = h->sg;
+    if (g.march2 && h->model == MM_MODEL_DEFAULT) {
+        if (g.wrap_on_load) return launch_sel2<MM_MODEL_DEFAULT, 1, 8, 0, true, 1>(h, a, mode, rot, vm, lean, write_g);
+        return launch_sel2<MM_MODEL_DEFAULT, 1, 8, 0, false, 1>(h, a, mode, rot, vm, lean, write_g);
+    }
+    if (h->model != MM_MODEL_ORIGINAL) {
+        set_error("the structured-grid kernels evaluate the 'default' model for one cell type, one state and one node mass only");
+        return MM_ERR_INVALID;
+    }
     if (g.march2) {
         const int pin = mode == M2_STEP ? g.pin_step : g.pin_force;
 #define X(R, T)                                                                                   \
     if (g.rpt == R && g.tile_rows == T) {                                                         \
-        if (!g.wrap_on_load) return launch_sel2<R, T, 0, false, 1>(h, a, mode, rot, vm, lean, write_g);               \
+        if (!g.wrap_on_load) return launch_sel2<MM_MODEL_ORIGINAL, R, T, 0, false, 1>(h, a, mode, rot, vm, lean, write_g);               \
         if (g.unroll == 2) {                                                                                          \
-            if (pin == 0) return launch_sel2<R, T, 0, true, 2>(h, a, mode, rot, vm, lean, write_g);                   \
-            return launch_sel2<R, T, 3, true, 2>(h, a, mode, rot, vm, lean, write_g);                                 \
+            if (pin == 0) return launch_sel2<MM_MODEL_ORIGINAL, R, T, 0, true, 2>(h, a, mode, rot, vm, lean, write_g);                   \
+            return launch_sel2<MM_MODEL_ORIGINAL, R, T, 3, true, 2>(h, a, mode, rot, vm, lean, write_g);                                 \
         }                                                                                                             \
-        if (pin == 0) return launch_sel2<R, T, 0, true, 1>(h, a, mode, rot, vm, lean, write_g);                       \
-        return launch_sel2<R, T, 3, true, 1>(h, a, mode, rot, vm, lean, write_g);                                     \
+        if (pin == 0) return launch_sel2<MM_MODEL_ORIGINAL, R, T, 0, true, 1>(h, a, mode, rot, vm, lean, write_g);                       \
+        return launch_sel2<MM_MODEL_ORIGINAL, R, T, 3, true, 1>(h, a, mode, rot, vm, lean, write_g);                                     \
     }
         MM_MARCH2_CONFIGS
 #undef X
@@ -949,6 +967,7 @@ int sg_set_tile_rows(mm_handle *h, int rows) {  // warps per block
 
 int sg_set_rpt(mm_handle *h, int rpt) {  // node rows per thread of k_march2
     SGrid &g = h->sg;
+    if (h->model == MM_MODEL_DEFAULT) return rpt == 1 ? MM_OK : MM_ERR_INVALID;
     if (!sg_march2_config_ok(rpt, g.tile_rows)) return MM_ERR_INVALID;
     g.rpt = rpt;
     return sg_retile(h, 0);

@@ -131,7 +131,8 @@ class ForcePartMechanical(ForcePart):
         self._keep = self._create()
         if structured is not None:
             _lib.check(self._lib.mm_set_option(self._handle, b"structured", int(bool(structured))))
-        for opt in ("variant",):  # kernel tuning knob MICMEC_B200_VARIANT=n
+        # kernel selection / tuning knobs, e.g. MICMEC_B200_MARCH2=0
+        for opt in ("march2", "wrap_on_load", "tail", "tail_in_kernel", "rows_per_thread", "variant"):
             env = os.environ.get("MICMEC_B200_" + opt.upper())
             if env is not None:
                 _lib.check(self._lib.mm_set_option(self._handle, opt.encode(), int(env)))

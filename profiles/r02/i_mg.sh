@@ -19,8 +19,8 @@ except Exception as e:
 PY
 }
 run npt_default --ensemble npt
-run npt_tik --ensemble npt --tail-in-kernel 1
-run npt_wrap0 --ensemble npt --wrap 0
+
+
 run nve_default --ensemble nve
-run nve_tik --ensemble nve --tail-in-kernel 1
-run nvt_default --ensemble nvt
+
+

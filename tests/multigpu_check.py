@@ -25,7 +25,7 @@ def build(system, ens, vel0, slab=None, device=0, ndof=None):
     from micmec_b200.sampling.npt import MTKBarostat, TBCombination
     from micmec_b200.units import femtosecond, pascal
 
-    part = ForcePartMechanical(system, device=device, structured=True, slab=slab)
+    part = ForcePartMechanical(system, model=os.environ.get("MULTIGPU_MODEL", "original"), device=device, structured=True, slab=slab)
     mmf = MicMecForceField(system, [part])
     hooks = []
     cvel = np.array([1e-4, -2e-4, 5e-5])

@@ -228,10 +228,16 @@ def two_type_params():
     return params
 
 
-@pytest.mark.parametrize("shape,mixed", [((12, 10, 8), False), ((33, 7, 5), False), ((40, 20, 70), False),
-                                         ((16, 12, 10), True), ((2, 2, 3), True)])
-def test_structured_kernels_match_generic_and_oracle(shape, mixed):
-    """The marching structured-grid kernel (mm_structured.cu) vs the indexed kernels vs the oracle."""
+@pytest.mark.parametrize("shape,mixed,model", [((12, 10, 8), False, "original"), ((33, 7, 5), False, "original"),
+                                               ((40, 20, 70), False, "original"), ((16, 12, 10), True, "original"),
+                                               ((2, 2, 3), True, "original"), ((12, 10, 8), False, "default"),
+                                               ((33, 7, 5), False, "default"), ((40, 20, 70), False, "default"),
+                                               ((2, 3, 2), False, "default")])
+@pytest.mark.parametrize("images", [0, 1])
+def test_structured_kernels_match_generic_and_oracle(shape, mixed, model, images, monkeypatch):
+    """The marching structured-grid kernels (k_march2 for one-type grids, k_march otherwise; periodic images from the
+    ghost nodes or taken on load) vs the indexed kernels vs the oracle, both per-cell models."""
+    monkeypatch.setenv("MICMEC_B200_WRAP_ON_LOAD", str(images))
     from micmec_b200.system import System
     from micmec_b200.celltypes import TYPE_FCU
 
@@ -251,7 +257,8 @@ def test_structured_kernels_match_generic_and_oracle(shape, mixed):
                       params=system.params, structured_shape=shape)
         from micmec_b200.pes.mmff import MicMecForceField, ForcePartMechanical
 
-        part = ForcePartMechanical(sysx, model="original", structured=structured)
+        part = ForcePartMechanical(sysx, model=model, structured=structured)
+        assert part.structured == structured
         mmf = MicMecForceField(sysx, [part])
         mmf.update_rvecs(rvecs)
         mmf.update_pos(pos)
@@ -264,7 +271,7 @@ def test_structured_kernels_match_generic_and_oracle(shape, mixed):
     assert abs(ea - eb) <= 1e-12 * abs(ea)
     assert gio.rel_rms(gb, ga) <= 1e-11
     assert gio.rel_rms(vb, va) <= 1e-11
-    oracle = orc.Oracle(system, model="original", nthreads=8)
+    oracle = orc.Oracle(system, model=model, nthreads=8)
     eo, go, vo = oracle.compute(pos, rvecs, gpos=True, vtens=True)
     _, gc, vc = oracle.deformation(pos, rvecs)
     check_against(eb, gb, vb, eo, go, vo, gio.virial_noise(gc, vc))

@@ -136,11 +136,14 @@ def test_matches_oracle_md_on_larger_grid(structured):
                 assert gio.rel_rms(thermo.chain.vel, md.chain_vel) <= 1e-7
 
 
-@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("path,model", [("march2", "original"), ("march2_images", "original"), ("march2_tail_in_kernel", "original"),
+                                        ("general", "original"), ("march2", "default"), ("march2_images", "default")])
 @pytest.mark.parametrize("ens", ["nve", "npt"])
-def test_structured_md_multitile_matches_indexed(ens, variant, monkeypatch):
-    """Fused marching kernel (register-prefetch and TMA variants) vs the indexed kernels on a grid that needs several
-    tiles in x (partial last tile, odd pitch), partial tiles in y and more than one chunk along z: 12 steps."""
+def test_structured_md_multitile_matches_indexed(ens, path, model, monkeypatch):
+    """Fused marching kernels vs the indexed kernels on a grid that needs several tiles in x (partial last tile, odd
+    pitch), partial tiles in y and more than one chunk along z: 12 steps.  Paths: k_march2 with ghost nodes (the
+    single-GPU default), with the periodic images taken on load + tail launch (the slab default), with the tail inside
+    the marching kernel, and the general kernel k_march; both per-cell models."""
     from micmec_b200.system import System
     from micmec_b200.celltypes import TYPE_FCU
     from micmec_b200.pes.mmff import MicMecForceField, ForcePartMechanical
@@ -149,7 +152,11 @@ def test_structured_md_multitile_matches_indexed(ens, variant, monkeypatch):
     from micmec_b200.sampling.npt import MTKBarostat, TBCombination
     from micmec_b200.units import femtosecond, pascal
 
-    monkeypatch.setenv("MICMEC_B200_VARIANT", str(variant))
+    env = {"march2": {"MICMEC_B200_WRAP_ON_LOAD": "0"}, "march2_images": {"MICMEC_B200_WRAP_ON_LOAD": "1"},
+           "march2_tail_in_kernel": {"MICMEC_B200_WRAP_ON_LOAD": "1", "MICMEC_B200_TAIL_IN_KERNEL": "1"},
+           "general": {"MICMEC_B200_MARCH2": "0"}}[path]
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
     shape = (37, 11, 41)
     rng = np.random.default_rng(21)
     base = System.periodic_grid(shape, TYPE_FCU, explicit=True)
@@ -160,7 +167,9 @@ def test_structured_md_multitile_matches_indexed(ens, variant, monkeypatch):
     for structured in (False, True):
         system = base if not structured else System.periodic_grid(shape, TYPE_FCU, explicit=False)
         system.pos[:] = pos0
-        mmf = MicMecForceField(system, [ForcePartMechanical(system, structured=structured)])
+        part = ForcePartMechanical(system, model=model, structured=structured)
+        assert part.structured == structured
+        mmf = MicMecForceField(system, [part])
         hooks = []
         if ens == "npt":
             thermo = NHCThermostat(300.0, timecon=100 * femtosecond, chain_vel0=np.array([1e-4, -2e-4, 5e-5]),

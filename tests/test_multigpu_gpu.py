@@ -20,11 +20,12 @@ def device_count():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("nproc,shape", [(2, "40,24,32"), (4, "40,24,32"), (8, "40,24,64")])
-def test_slab_decomposition_matches_single_gpu(nproc, shape):
+@pytest.mark.parametrize("nproc,shape,model", [(2, "40,24,32", "original"), (4, "40,24,32", "original"), (8, "40,24,64", "original"),
+                                               (2, "40,24,32", "default")])
+def test_slab_decomposition_matches_single_gpu(nproc, shape, model):
     if device_count() < nproc:
         pytest.skip("needs %d GPUs" % nproc)
-    env = dict(os.environ, MULTIGPU_SHAPE=shape)
+    env = dict(os.environ, MULTIGPU_SHAPE=shape, MULTIGPU_MODEL=model)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
            "127.0.0.1", "--master-port", str(29540 + nproc), os.path.join(ROOT, "tests", "multigpu_check.py")]
     proc = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
