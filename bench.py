@@ -50,16 +50,10 @@ def parse_args():
     ap.add_argument("--cpu-grid", type=int, default=48, help="edge of the bounded CPU sample grid")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--tile-rows", type=int, default=0, help="tuning: warps per block of the marching kernel (8/12/16)")
-    ap.add_argument("--variant", type=int, default=-1, help="tuning bits of the marching kernel (1 pairwise barriers, 2 TMA loads, 4 two planes per trip, 8 one barrier per plane)")
     ap.add_argument("--chunk", type=int, default=0, help="tuning: planes per block along z")
-    ap.add_argument("--rpt", type=int, default=0, help="tuning: node rows per thread of k_march2 (1/2/3)")
     ap.add_argument("--wrap", type=int, default=-1, help="tuning: 0 = k_march2 reads the periodic images from the ghost nodes")
-    ap.add_argument("--unroll", type=int, default=-1, help="tuning: planes per trip of k_march2's steady loop (1/2)")
     ap.add_argument("--tail-in-kernel", type=int, default=-1, help="tuning: 1 = the last block of a marching launch runs the tail")
     ap.add_argument("--tail", type=int, default=-1, help="tuning: 0 = reduction / exchange / scalar algebra in their own launches")
-    ap.add_argument("--pin-step", type=int, default=-1, help="tuning: 0 / 3 rows of Bq in per-thread registers, STEP launches")
-    ap.add_argument("--pin-force", type=int, default=-1, help="tuning: likewise for the force-only launches")
     ap.add_argument("--march2", type=int, default=-1, help="tuning: 0 = keep the general kernel k_march for the one-type grids too")
     ap.add_argument("--generic", action="store_true", help="force the indexed-topology kernels (no structured path)")
     return ap.parse_args()
@@ -272,17 +266,11 @@ def main():
         part = ForcePartMechanical(system, model=args.model, device=local_rank, slab=layout.slab_arg())
     if args.march2 >= 0:
         _lib.check(lib.mm_set_option(part.handle, b"march2", args.march2))
-    if args.rpt:
-        _lib.check(lib.mm_set_option(part.handle, b"rows_per_thread", args.rpt))
-    for name, val in (("wrap_on_load", args.wrap), ("unroll", args.unroll), ("tail", args.tail), ("tail_in_kernel", args.tail_in_kernel), ("pin_step", args.pin_step), ("pin_force", args.pin_force)):
+    for name, val in (("wrap_on_load", args.wrap), ("tail", args.tail), ("tail_in_kernel", args.tail_in_kernel)):
         if val >= 0:
             _lib.check(lib.mm_set_option(part.handle, name.encode(), val))
-    if args.tile_rows:
-        _lib.check(lib.mm_set_option(part.handle, b"tile_rows", args.tile_rows))
     if args.chunk:
         _lib.check(lib.mm_set_option(part.handle, b"chunk", args.chunk))
-    if args.variant >= 0:
-        _lib.check(lib.mm_set_option(part.handle, b"variant", args.variant))
     mmf = MicMecForceField(system, [part])
     stream = torch.cuda.Stream(device=local_rank)
     _lib.check(lib.mm_set_stream(part.handle, ctypes.c_void_p(stream.cuda_stream)))

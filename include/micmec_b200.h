@@ -162,6 +162,12 @@ typedef struct {
     int32_t has_baro;
     int32_t anisotropic, vol_constraint;
     double baro_temp, baro_press, baro_timecon;
+    /* Langevin thermostat on the device (nvt.py:165-218; instead of the Nose-Hoover chain, without a barostat).  The noise
+     * comes from a counter-based generator (Philox4x32-10 keyed by seed, node id and half-step number): the same node gets
+     * the same kick on every GPU and in every kernel layout, but the stream is not NumPy's - parity is statistical. */
+    int32_t has_langevin, langevin_pad;
+    double langevin_temp, langevin_timecon;
+    uint64_t langevin_seed;
     double time0;      /* VerletIntegrator(time0=...), verlet.py:96: simulation time at initialisation (restarts) */
     int64_t counter0;  /* VerletIntegrator(counter0=...), iterative.py: step counter at initialisation */
 } mm_md_desc;

@@ -71,6 +71,11 @@ class MDDesc(ctypes.Structure):
         ("baro_temp", ctypes.c_double),
         ("baro_press", ctypes.c_double),
         ("baro_timecon", ctypes.c_double),
+        ("has_langevin", ctypes.c_int32),
+        ("langevin_pad", ctypes.c_int32),
+        ("langevin_temp", ctypes.c_double),
+        ("langevin_timecon", ctypes.c_double),
+        ("langevin_seed", ctypes.c_uint64),
         ("time0", ctypes.c_double),
         ("counter0", ctypes.c_int64),
     ]

@@ -409,10 +409,6 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value) {
         h->sg.tail_wanted = value ? 1 : 0;
         return MM_OK;
     }
-    if (strcmp(name, "unroll") == 0) {
-        h->sg.unroll = value == 2 ? 2 : 1;
-        return MM_OK;
-    }
     if (strcmp(name, "wrap_on_load") == 0) {
         h->sg.wrap_wanted = value < 0 ? -1 : (value ? 1 : 0);
         if (!h->sg.d_sc) return MM_OK;
@@ -422,10 +418,6 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value) {
     }
     if (strcmp(name, "tail_in_kernel") == 0) {
         h->sg.tail_in_kernel = value ? 1 : 0;
-        return MM_OK;
-    }
-    if (strcmp(name, "pin_step") == 0 || strcmp(name, "pin_force") == 0) {
-        (name[4] == 's' ? h->sg.pin_step : h->sg.pin_force) = value ? 3 : 0;
         return MM_OK;
     }
     return invalid(std::string("mm_set_option: unknown option ") + name);

@@ -30,8 +30,9 @@ namespace mm {
 // canonical order RESET_MVEL, TAKE_FORCE, TAKE_KIN, BARO_B, THERMO, BARO_A, ECONS, PROPS (see md_step below).
 __global__ void __launch_bounds__(256)
 k_scalar(MDState *st, double *rvecs_dev, StepConsts *sc, unsigned ops, const double *pc, int nbc, const double *pn, int nbn,
-         const double *pd, int nbd, double n3) {
-    double fr[7] = {0, 0, 0, 0, 0, 0, 0}, kn[7] = {0, 0, 0, 0, 0, 0, 0}, dl[1] = {0};
+         const double *pd, int nbd, double n3, const double *pl, int nbl) {
+    double fr[7] = {0, 0, 0, 0, 0, 0, 0}, kn[7] = {0, 0, 0, 0, 0, 0, 0}, dl[1] = {0}, lg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if ((ops & (OP_LANG_A | OP_LANG_B)) && nbl > 0) partials_sum<8>(pl, nbl, kRedSlots, lg);
     if (pn == pc + 7 && nbn == nbc && nbc > 1 && (ops & (OP_TAKE_KIN | OP_TAKE_FORCE))) {
         double all[16];  // structured path: both halves live in the same 16-slot records
         partials_sum16(pc, nbc, all);
@@ -52,7 +53,7 @@ k_scalar(MDState *st, double *rvecs_dev, StepConsts *sc, unsigned ops, const dou
     for (int i = threadIdx.x; i < kWords; i += blockDim.x)
         reinterpret_cast<double *>(&sm_state)[i] = reinterpret_cast<const double *>(st)[i];
     __syncthreads();
-    if (threadIdx.x == 0) scalar_ops(sm_state, rvecs_dev, sc, ops, fr, kn, dl, nbn, n3);
+    if (threadIdx.x == 0) scalar_ops(sm_state, rvecs_dev, sc, ops, fr, kn, dl, nbn, n3, lg);
     __syncthreads();
     for (int i = threadIdx.x; i < kWords; i += blockDim.x)
         reinterpret_cast<double *>(st)[i] = reinterpret_cast<const double *>(&sm_state)[i];
@@ -60,6 +61,127 @@ k_scalar(MDState *st, double *rvecs_dev, StepConsts *sc, unsigned ops, const dou
 
 // --------------------------------------------------------------------------------------- node kernels --------
 constexpr int kNodeThreads = 256;
+constexpr int kNodeThreadsL = 256;
+
+// ---- Langevin thermostat on the device (nvt.py:165-218) ----------------------------------------------------------------
+// v <- c1 v + c2 xi with c1 = exp(-dt / (2 timecon)), c2 = sqrt((1 - c1^2) kB T / m), xi ~ N(0, 1) per component.
+// xi comes from Philox4x32-10 (Salmon et al., SC'11) keyed by the seed and counted by (reference node id, half-step
+// number, draw): a node gets the same kick wherever a copy of it lives - ghost nodes, halo planes of a z-slab, the AoS
+// arrays of the indexed kernels - so no exchange follows the update, and structured and indexed runs of one seed agree.
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned (&out)[4]) {
+#pragma unroll
+    for (int round = 0; round < 10; round++) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (unsigned)p1;
+        c3 = (unsigned)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// three standard normal deviates of node `gid` at half-step `phase` (Box-Muller on 64-bit uniforms)
+__device__ __forceinline__ void langevin_noise(unsigned long long seed, long long gid, long long phase, double (&xi)[3]) {
+    double z[4];
+#pragma unroll
+    for (int draw = 0; draw < 2; draw++) {
+        unsigned r[4];
+        philox4x32_10((unsigned)gid, (unsigned)((unsigned long long)gid >> 32), (unsigned)phase,
+                      (unsigned)(((unsigned long long)phase >> 32) << 1) | (unsigned)draw, (unsigned)seed, (unsigned)(seed >> 32), r);
+        const double u1 = ((double)(((unsigned long long)r[0] << 32) | r[1]) + 0.5) * 5.421010862427522e-20;  // 2^-64
+        const double u2 = ((double)(((unsigned long long)r[2] << 32) | r[3]) + 0.5) * 5.421010862427522e-20;
+        const double rad = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        z[2 * draw] = rad * cs;
+        z[2 * draw + 1] = rad * sn;
+    }
+    xi[0] = z[0];
+    xi[1] = z[1];
+    xi[2] = z[2];
+}
+
+struct LangArgs {
+    double *v[3];        // structured: SoA planes (all padded nodes are updated, copies included); indexed: v[0] = vel [n][3]
+    const double *m;     // node masses in the same layout
+    int structured;
+    int nx, ny, nzl, nxp, z0, nz_global;
+    long long plane, n;  // padded plane / number of entries to visit
+    double kT;           // kB T
+    int nphase;          // 1: one half-step; 2: a "post" followed by the next step's "pre"
+    int phase_offset;    // half-step number = 2 * (steps completed) + offset: 0 for a lone "pre", 1 for a "post"
+};
+
+__global__ void __launch_bounds__(kNodeThreadsL)
+k_langevin(const __grid_constant__ LangArgs a, const MDState *__restrict__ st, double *__restrict__ partials) {
+    const double c1 = exp(-st->timestep / st->lg_timecon / 2.0);
+    const double var = (1.0 - c1 * c1) * a.kT;
+    const long long phase0 = 2 * st->counter + a.phase_offset;
+    const unsigned long long seed = st->lg_seed;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        long long gid;
+        bool owned = true;
+        double vx, vy, vz, mass;
+        if (a.structured) {
+            const int p = (int)(i / a.plane);
+            const long long rem = i - (long long)p * a.plane;
+            const int lrow = (int)(rem / a.nxp), kcol = (int)(rem - (long long)lrow * a.nxp);
+            const int k = kcol - kGhostX, l = lrow - 1;
+            if (k < -1 || k > a.nx || l > a.ny) continue;  // pad columns
+            const int kw = (k + a.nx) % a.nx, lw = (l + a.ny) % a.ny, pz = (a.z0 + p - 1 + a.nz_global) % a.nz_global;
+            gid = ((long long)kw * a.ny + lw) * a.nz_global + pz;  // reference id (micmec/utils.py:226)
+            owned = k >= 0 && k < a.nx && l >= 0 && l < a.ny && p >= 1 && p <= a.nzl;
+            vx = a.v[0][i];
+            vy = a.v[1][i];
+            vz = a.v[2][i];
+            mass = a.m[i];
+        } else {
+            gid = i;
+            vx = a.v[0][3 * i];
+            vy = a.v[0][3 * i + 1];
+            vz = a.v[0][3 * i + 2];
+            mass = a.m[i];
+        }
+        if (!(mass > 0.0)) continue;  // unused padded entries
+        const double c2 = sqrt(var / mass), w = owned ? mass : 0.0;
+        acc[0] += w * (vx * vx + vy * vy + vz * vz);
+        double xi[3];
+        langevin_noise(seed, gid, phase0, xi);
+        vx = fma(c2, xi[0], c1 * vx);
+        vy = fma(c2, xi[1], c1 * vy);
+        vz = fma(c2, xi[2], c1 * vz);
+        acc[1] += w * vx * vx;
+        acc[2] += w * vy * vy;
+        acc[3] += w * vz * vz;
+        acc[4] += w * vy * vz;
+        acc[5] += w * vx * vz;
+        acc[6] += w * vx * vy;
+        if (a.nphase == 2) {
+            langevin_noise(seed, gid, phase0 + 1, xi);
+            vx = fma(c2, xi[0], c1 * vx);
+            vy = fma(c2, xi[1], c1 * vy);
+            vz = fma(c2, xi[2], c1 * vz);
+            acc[7] += w * (vx * vx + vy * vy + vz * vz);
+        }
+        if (a.structured) {
+            a.v[0][i] = vx;
+            a.v[1][i] = vy;
+            a.v[2][i] = vz;
+        } else {
+            a.v[0][3 * i] = vx;
+            a.v[0][3 * i + 1] = vy;
+            a.v[0][3 * i + 2] = vz;
+        }
+    }
+    block_sum_store<8>(acc, partials + (size_t)blockIdx.x * kRedSlots);
+}
 
 // v <- v.Mvel - (dt/2) g/m ; x <- x + dt v      (hook scalings + verlet.py:144-146); optional posold snapshot
 __global__ void __launch_bounds__(kNodeThreads)
@@ -222,6 +344,8 @@ struct mm_md {
     double *d_vel = nullptr, *d_masses = nullptr, *d_posold = nullptr;
     double *d_pkin = nullptr;    // partials of node kernels [kMaxRedBlocks][kRedSlots]
     double *d_pdelta = nullptr;  // partials of k_delta
+    double *d_plang = nullptr;   // partials of k_langevin
+    int nblang = 0;              // ... pending for the next scalar launch
     bool initialised = false;
     bool structured = false;  // state lives in the SoA planes of h->sg
     // CUDA graphs of TWO consecutive lean steps (two, because the ping-pong buffers return to the same parity after
@@ -237,6 +361,8 @@ namespace mm {
 
 static int scalar_launch(mm_md *md, unsigned ops, int nbc, int nbn, int nbd) {
     mm_handle *h = md->h;
+    const int nbl = md->nblang;  // sums of a k_langevin launch waiting to be booked (OP_LANG_A / OP_LANG_B)
+    md->nblang = 0;
     const bool sg = md->structured;
     // structured kernels leave all 14 sums of a block in one partial: energy + virial in slots 0-6, moments + g^2 in 7-13
     const double *pc = sg ? h->sg.d_partials : h->d_partials;
@@ -255,8 +381,41 @@ static int scalar_launch(mm_md *md, unsigned ops, int nbc, int nbn, int nbd) {
         nbd = nbd > 0 ? 1 : 0;
     }
     k_scalar<<<1, 256, 0, h->stream>>>(md->d_state, h->d_rvecs, sg ? h->sg.d_sc : nullptr, ops, pc, nbc, pn, nbn, pd, nbd,
-                                       3.0 * (double)h->nnodes_global);
+                                       3.0 * (double)h->nnodes_global, md->d_plang, nbl);
     h->launches++;
+    return MM_OK;
+}
+
+// Langevin half-step(s) on the current velocities (nvt.py:199-218); the sums wait in d_plang for the next scalar launch
+static int lang_launch(mm_md *md, int nphase, int phase_offset) {
+    mm_handle *h = md->h;
+    LangArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nphase = nphase;
+    a.phase_offset = phase_offset;
+    a.kT = h->boltzmann * md->desc.langevin_temp;
+    if (md->structured) {
+        const SGrid &g = h->sg;
+        a.structured = 1;
+        for (int d = 0; d < 3; d++) a.v[d] = g.v[g.cv][d];
+        a.m = g.m;
+        a.nx = g.nx;
+        a.ny = g.ny;
+        a.nzl = g.nzl;
+        a.nxp = g.nxp;
+        a.plane = g.plane;
+        a.z0 = h->slab_rank * g.nzl;
+        a.nz_global = g.nzl * (h->slab_count > 1 ? h->slab_count : 1);
+        a.n = g.plane * (g.nzl + 2);
+    } else {
+        a.v[0] = md->d_vel;
+        a.m = md->d_masses;
+        a.n = h->nnodes;
+    }
+    const int gl = grid_for(h, a.n, kNodeThreadsL);
+    k_langevin<<<gl, kNodeThreadsL, 0, h->stream>>>(a, md->d_state, md->d_plang);
+    h->launches++;
+    md->nblang = gl;
     return MM_OK;
 }
 
@@ -278,7 +437,7 @@ static int baro_force(mm_md *md, bool snapshot, int &nbc, int &nbn) {
 // merge_next: append the NEXT step's first "pre" call to this step's last scalar launch (only between lean steps).
 static int md_step(mm_md *md, bool full, bool own_pre, bool merge_next) {
     mm_handle *h = md->h;
-    const bool thermo = md->desc.has_thermo != 0, baro = md->desc.has_baro != 0;
+    const bool thermo = md->desc.has_thermo != 0, baro = md->desc.has_baro != 0, lang = md->desc.has_langevin != 0;
     const int gn = grid_for(h, h->nnodes, kNodeThreads);
     int nbc = 0, nbn = 0;
     // ---- "pre" hooks: TBCombination.pre = barostat, then thermostat (npt.py:99-115) ----
@@ -288,8 +447,11 @@ static int md_step(mm_md *md, bool full, bool own_pre, bool merge_next) {
         scalar_launch(md, OP_TAKE_FORCE | OP_BARO_B | (thermo ? OP_THERMO : 0u), nbc, nbn, 0);
     } else if (thermo) {
         if (own_pre) scalar_launch(md, OP_THERMO, 0, 0, 0);
+    } else if (lang && own_pre) {
+        lang_launch(md, 1, 0);
+        scalar_launch(md, OP_LANG_A, 0, 0, 0);
     }
-    const unsigned next_op = !merge_next ? 0u : baro ? OP_NEXT_BARO_A : thermo ? OP_NEXT_THERMO : 0u;
+    const unsigned next_op = !merge_next ? 0u : baro ? OP_NEXT_BARO_A : thermo ? OP_NEXT_THERMO : lang ? OP_LANG_B : 0u;
     // ---- velocity Verlet (verlet.py:144-154) ----
     k_kick_drift<<<gn, kNodeThreads, 0, h->stream>>>(md->d_state, h->d_pos, md->d_vel, h->d_gpos, md->d_masses,
                                                      (full && !baro) ? md->d_posold : nullptr, h->nnodes);
@@ -307,6 +469,10 @@ static int md_step(mm_md *md, bool full, bool own_pre, bool merge_next) {
             k_delta<<<nbd, kNodeThreads, 0, h->stream>>>(h->d_pos, md->d_posold, 3 * h->nnodes, md->d_pdelta);
             h->launches++;
             ops |= OP_TAKE_DELTA;
+        }
+        if (lang) {  // "post" (and, between lean steps, the next step's "pre" in the same pass)
+            lang_launch(md, merge_next ? 2 : 1, 1);
+            ops |= OP_LANG_A;
         }
         scalar_launch(md, ops | OP_ECONS | OP_ADVANCE | OP_PROPS | next_op, nbc, gn, nbd);
     } else {
@@ -358,10 +524,10 @@ static void sg_export(mm_md *md, bool pos, bool vel, double *pos_dst) {
 // force-only launch per barostat call.  Pending rotations / scalings are consumed by the kernels on load.
 static int md_step_structured(mm_md *md, bool full, bool own_pre, bool merge_next) {
     mm_handle *h = md->h;
-    const bool thermo = md->desc.has_thermo != 0, baro = md->desc.has_baro != 0;
+    const bool thermo = md->desc.has_thermo != 0, baro = md->desc.has_baro != 0, lang = md->desc.has_langevin != 0;
     const int nb = h->sg.nblocks;
-    const unsigned next_op = !merge_next ? 0u : baro ? OP_NEXT_BARO_A : thermo ? OP_NEXT_THERMO : 0u;
-    if (!full && sg_tail_ok(h)) {
+    const unsigned next_op = !merge_next ? 0u : baro ? OP_NEXT_BARO_A : thermo ? OP_NEXT_THERMO : lang ? OP_LANG_B : 0u;
+    if (!full && sg_tail_ok(h) && !lang) {
         // Lean step on the fast path: every marching launch ends with its own reduction, slab exchange and scalar algebra
         // (tail of k_march2), and takes the periodic images on load - no launch between two marching kernels.
         SgTail t;
@@ -394,6 +560,9 @@ static int md_step_structured(mm_md *md, bool full, bool own_pre, bool merge_nex
         sg_halo(h, true, false, true);  // after OP_POS_WRITTEN: the halo shift uses the new stored frame
     } else if (thermo) {
         if (own_pre) scalar_launch(md, OP_THERMO, 0, 0, 0);
+    } else if (lang && own_pre) {
+        lang_launch(md, 1, 0);
+        scalar_launch(md, OP_LANG_A, 0, 0, 0);
     }
     // without a barostat the gradient written here feeds the next step's first kick
     sg_step(h, !baro, baro ? 2 : (thermo ? 1 : 0), !full);
@@ -407,6 +576,10 @@ static int md_step_structured(mm_md *md, bool full, bool own_pre, bool merge_nex
             k_delta<<<nbd, kNodeThreads, 0, h->stream>>>(h->d_pos, md->d_posold, 3 * h->nnodes, md->d_pdelta);
             h->launches++;
             ops |= OP_TAKE_DELTA;
+        }
+        if (lang) {  // every copy of a node (ghosts, halo planes) gets the same kick: no exchange afterwards
+            lang_launch(md, merge_next ? 2 : 1, 1);
+            ops |= OP_LANG_A;
         }
         scalar_launch(md, ops | OP_ECONS | OP_ADVANCE | OP_PROPS | next_op, nb, nb, nbd);
     } else {
@@ -441,6 +614,7 @@ int mm_md_destroy(mm_md *md) {
     cudaFree(md->d_posold);
     cudaFree(md->d_pkin);
     cudaFree(md->d_pdelta);
+    cudaFree(md->d_plang);
     if (md->h_state) cudaFreeHost(md->h_state);
     for (int i = 0; i < 8; i++)
         if (md->gexec[i]) cudaGraphExecDestroy(md->gexec[i]);
@@ -466,6 +640,10 @@ int mm_md_create(mm_handle *h, const mm_md_desc *desc, mm_md **out) {
         set_error("mm_md_create: timestep must be positive");
         return MM_ERR_INVALID;
     }
+    if (desc->has_langevin && (desc->has_thermo || desc->has_baro || h->slab_count > 1 || !(desc->langevin_timecon > 0.0))) {
+        set_error("mm_md_create: the device Langevin thermostat runs alone (no chain, no barostat) on one GPU");
+        return MM_ERR_INVALID;
+    }
     mm_md *md = new (std::nothrow) mm_md();
     if (!md) return MM_ERR_INVALID;
     md->h = h;
@@ -487,6 +665,7 @@ int mm_md_create(mm_handle *h, const mm_md_desc *desc, mm_md **out) {
     MM_TRY(cudaMalloc(&md->d_posold, sizeof(double) * 3 * nn));
     MM_TRY(cudaMalloc(&md->d_pkin, sizeof(double) * kMaxRedBlocks * kRedSlots));
     MM_TRY(cudaMalloc(&md->d_pdelta, sizeof(double) * kMaxRedBlocks * kRedSlots));
+    MM_TRY(cudaMalloc(&md->d_plang, sizeof(double) * kMaxRedBlocks * kRedSlots));
     MM_TRY(cudaHostAlloc(&md->h_state, sizeof(MDState), cudaHostAllocDefault));
 #undef MM_TRY
     *out = md;
@@ -532,6 +711,10 @@ int mm_md_init(mm_md *md, const double *pos, const double *vel, const double *ma
         s.ch_pos[k] = chain_pos ? chain_pos[k] : 0.0;
         s.ch_vel[k] = chain_vel ? chain_vel[k] : 0.0;
     }
+    s.has_langevin = d.has_langevin;
+    s.lg_temp = d.langevin_temp;
+    s.lg_timecon = d.langevin_timecon;
+    s.lg_seed = d.langevin_seed;
     s.has_baro = d.has_baro;
     s.aniso = d.anisotropic;
     s.volc = d.vol_constraint;

@@ -43,6 +43,10 @@ struct MDState {
     double econs_corr;
     long long ce_n;
     double ce_ekin_m, ce_ekin_s, ce_econs_m, ce_econs_s;
+    // Langevin thermostat (nvt.py:165-218): accumulated econs_correction = sum of (ekin before - ekin after) of every call
+    int has_langevin, lg_pad;
+    double lg_temp, lg_timecon, lg_corr;
+    unsigned long long lg_seed;
     // properties (verlet.py:171-190)
     double temp, etot, econs, cons_err, press, ptens[9], rmsd_gpos, rmsd_delta, volume;
 };
@@ -63,6 +67,8 @@ enum : unsigned {
     OP_POS_WRITTEN = 1u << 12,
     OP_NEXT_THERMO = 1u << 13,  // the NEXT step's thermostat "pre" call, merged into this step's last scalar launch
     OP_NEXT_BARO_A = 1u << 14,  // the NEXT step's first barostat half, likewise
+    OP_LANG_A = 1u << 15,       // Langevin thermostat: book the first half-step of a k_langevin launch (a "post", or a lone "pre")
+    OP_LANG_B = 1u << 16,       // ... and its second half-step (the NEXT step's "pre", merged into the same launch)
 };
 
 // ------------------------------------------------------------------------------------------- 3x3 helpers ----
@@ -290,6 +296,7 @@ static __device__ void econs_update(MDState &s) {
         if (!s.volc) corr += s.b_press * volume_of(s.rvecs);
         if (s.has_thermo) corr += s.baro_ndof * kb * s.ch_temp * s.ch_pos[0];
     }
+    if (s.has_langevin) corr += s.lg_corr;
     s.econs_corr = corr;
 }
 
@@ -323,8 +330,10 @@ static __device__ void properties(MDState &s, double n3) {  // verlet.py:171-190
     }
 }
 
+// lg: sums of one k_langevin launch - [0] sum m v^2 before, [1..6] sum m v (x) v after its first half-step, [7] sum m v^2 after
+// its second half-step (nvt.py:199-218: econs_correction += ekin0 - ekin1 around every call)
 static __device__ __noinline__ void scalar_ops(MDState &s, double *rvecs_dev, StepConsts *sc, unsigned ops, const double *fr, const double *kn,
-                           const double *dl, int nbn, double n3) {
+                           const double *dl, int nbn, double n3, const double *lg = nullptr) {
     if (ops & OP_RESET_MVEL)
         for (int i = 0; i < 9; i++) s.Mvel[i] = (i % 4 == 0) ? 1.0 : 0.0;
     if (ops & OP_POS_WRITTEN)  // the stored positions are the true ones again
@@ -368,12 +377,22 @@ static __device__ __noinline__ void scalar_ops(MDState &s, double *rvecs_dev, St
         baro_a(s);
         for (int i = 0; i < 9; i++) rvecs_dev[i] = s.rvecs[i];
     }
+    if ((ops & OP_LANG_A) && lg) {
+        const double after = 0.5 * (lg[1] + lg[2] + lg[3]);
+        s.lg_corr += 0.5 * lg[0] - after;
+        for (int k = 0; k < 6; k++) s.mvv[k] = lg[1 + k];
+        s.ekin = after;
+    }
     if (ops & OP_ECONS) econs_update(s);
     if (ops & OP_ADVANCE) {
         s.time += s.timestep;
         s.counter++;
     }
     if (ops & OP_PROPS) properties(s, n3);
+    if ((ops & OP_LANG_B) && lg) {
+        s.lg_corr += 0.5 * (lg[1] + lg[2] + lg[3]) - 0.5 * lg[7];
+        s.ekin = 0.5 * lg[7];
+    }
     if (ops & OP_NEXT_THERMO) thermo_call(s);
     if (ops & OP_NEXT_BARO_A) {
         baro_a(s);

@@ -837,75 +837,54 @@ static int launch_one2(mm_handle *h, const MarchArgs &a, int write_g) {
     return MM_OK;
 }
 
-// mode: M2_FORCE / M2_STEP / M2_VIRIAL (energy + virial only; rot 1)
-template <int MODEL, int RPT, int TY, int PIN, bool WRAP, int UNR>
+// mode: M2_FORCE / M2_STEP / M2_VIRIAL (energy + virial only; rot 1).  Rows of Bq in per-thread registers (PIN, measured
+// in profiles/r02/d, g): none for the fused step (its register budget is exhausted: 588 -> 60 bytes of spills), three for the
+// force-only launches of the averaged model.
+template <int MODEL, int RPT, int TY, bool WRAP>
 static int launch_sel2(mm_handle *h, const MarchArgs &a, int mode, int rot, int vm, bool lean, int write_g) {
+    constexpr int PS = 0, PF = MODEL == MM_MODEL_DEFAULT ? 0 : 3;
     if (mode == M2_STEP) {
         if (lean) {
-            if (vm == 0) return launch_one2<MODEL, M2_STEP, 0, 0, true, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
-            return launch_one2<MODEL, M2_STEP, 0, 1, true, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+            if (vm == 0) return launch_one2<MODEL, M2_STEP, 0, 0, true, RPT, TY, PS, WRAP, 1>(h, a, write_g);
+            return launch_one2<MODEL, M2_STEP, 0, 1, true, RPT, TY, PS, WRAP, 1>(h, a, write_g);
         }
-        if (vm == 0) return launch_one2<MODEL, M2_STEP, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
-        if (vm == 1) return launch_one2<MODEL, M2_STEP, 0, 1, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
-        return launch_one2<MODEL, M2_STEP, 0, 2, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+        if (vm == 0) return launch_one2<MODEL, M2_STEP, 0, 0, false, RPT, TY, PS, WRAP, 1>(h, a, write_g);
+        if (vm == 1) return launch_one2<MODEL, M2_STEP, 0, 1, false, RPT, TY, PS, WRAP, 1>(h, a, write_g);
+        return launch_one2<MODEL, M2_STEP, 0, 2, false, RPT, TY, PS, WRAP, 1>(h, a, write_g);
     }
     if (mode == M2_VIRIAL) {
-        if (rot == 0) return launch_one2<MODEL, M2_VIRIAL, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, 0);
-        return launch_one2<MODEL, M2_VIRIAL, 1, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, 0);
+        if (rot == 0) return launch_one2<MODEL, M2_VIRIAL, 0, 0, false, RPT, TY, PF, WRAP, 1>(h, a, 0);
+        return launch_one2<MODEL, M2_VIRIAL, 1, 0, false, RPT, TY, PF, WRAP, 1>(h, a, 0);
     }
-    if (rot == 0) return launch_one2<MODEL, M2_FORCE, 0, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
-    if (rot == 1) return launch_one2<MODEL, M2_FORCE, 1, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
-    return launch_one2<MODEL, M2_FORCE, 2, 0, false, RPT, TY, PIN, WRAP, UNR>(h, a, write_g);
+    if (rot == 0) return launch_one2<MODEL, M2_FORCE, 0, 0, false, RPT, TY, PF, WRAP, 1>(h, a, write_g);
+    if (rot == 1) return launch_one2<MODEL, M2_FORCE, 1, 0, false, RPT, TY, PF, WRAP, 1>(h, a, write_g);
+    return launch_one2<MODEL, M2_FORCE, 2, 0, false, RPT, TY, PF, WRAP, 1>(h, a, write_g);
 }
 
-#ifndef MM_MARCH2_CONFIGS  // (rows per thread, warps) pairs compiled into the library; the first one is the default
-#define MM_MARCH2_CONFIGS X(2, 8)
-#endif
-
-bool sg_march2_config_ok(int rpt, int ty) {
-    if (rpt == 1 && ty == 8) return true;  // the default-model instantiation
-#define X(R, T) if (rpt == R && ty == T) return true;
-    MM_MARCH2_CONFIGS
-#undef X
-    return false;
-}
+// tile of the averaged model: 2 node rows per thread x 8 warps (30 x 14 owned nodes); profiles/r02/c has the alternatives
+// (1 x 8: +10 %, 3 x 8: register spills, +40 %; 2 x 4 with two blocks per SM: +8 %).  The eight-corner model keeps one row.
+bool sg_march2_config_ok(int rpt, int ty) { return (rpt == 2 || rpt == 1) && ty == 8; }
 
 static int launch_march(mm_handle *h, const MarchArgs &a, int mode, int rot, int vm, bool lean, int write_g) {
     const SGrid &g = h->sg;
     if (g.march2 && h->model == MM_MODEL_DEFAULT) {
-        if (g.wrap_on_load) return launch_sel2<MM_MODEL_DEFAULT, 1, 8, 0, true, 1>(h, a, mode, rot, vm, lean, write_g);
-        return launch_sel2<MM_MODEL_DEFAULT, 1, 8, 0, false, 1>(h, a, mode, rot, vm, lean, write_g);
+        if (g.wrap_on_load) return launch_sel2<MM_MODEL_DEFAULT, 1, 8, true>(h, a, mode, rot, vm, lean, write_g);
+        return launch_sel2<MM_MODEL_DEFAULT, 1, 8, false>(h, a, mode, rot, vm, lean, write_g);
     }
     if (h->model != MM_MODEL_ORIGINAL) {
         set_error("the structured-grid kernels evaluate the 'default' model for one cell type, one state and one node mass only");
         return MM_ERR_INVALID;
     }
     if (g.march2) {
-        const int pin = mode == M2_STEP ? g.pin_step : g.pin_force;
-#define X(R, T)                                                                                   \
-    if (g.rpt == R && g.tile_rows == T) {                                                         \
-        if (!g.wrap_on_load) return launch_sel2<MM_MODEL_ORIGINAL, R, T, 0, false, 1>(h, a, mode, rot, vm, lean, write_g);               \
-        if (g.unroll == 2) {                                                                                          \
-            if (pin == 0) return launch_sel2<MM_MODEL_ORIGINAL, R, T, 0, true, 2>(h, a, mode, rot, vm, lean, write_g);                   \
-            return launch_sel2<MM_MODEL_ORIGINAL, R, T, 3, true, 2>(h, a, mode, rot, vm, lean, write_g);                                 \
-        }                                                                                                             \
-        if (pin == 0) return launch_sel2<MM_MODEL_ORIGINAL, R, T, 0, true, 1>(h, a, mode, rot, vm, lean, write_g);                       \
-        return launch_sel2<MM_MODEL_ORIGINAL, R, T, 3, true, 1>(h, a, mode, rot, vm, lean, write_g);                                     \
-    }
-        MM_MARCH2_CONFIGS
-#undef X
-        set_error("k_march2: tile configuration not compiled into this library");
-        return MM_ERR_INVALID;
+        if (g.wrap_on_load) return launch_sel2<MM_MODEL_ORIGINAL, 2, 8, true>(h, a, mode, rot, vm, lean, write_g);
+        return launch_sel2<MM_MODEL_ORIGINAL, 2, 8, false>(h, a, mode, rot, vm, lean, write_g);
     }
     const bool step = mode == M2_STEP;
     const bool single = g.sp.ntypes == 1 && g.sp.nstates[0] == 1;
     // general path: several cell types / metastable states / node masses (register-prefetch loads, mass arrays)
-    if (single) {
-#ifdef MM_KEEP_V14  // the round-1 kernel (TMA loads, one barrier per plane, two planes per trip): A/B builds only
-        if ((g.variant & 15) == 14 && g.tma_ok) return launch_sel<true, 14>(h, a, step, rot, vm, lean, write_g);
-#endif
-        return launch_sel<true, 0>(h, a, step, rot, vm, lean, write_g);
-    }
+    // (the tuning variants of k_march measured in round 1 - TMA staging, pairwise barriers, two planes per trip - are not
+    // instantiated in the product library any more: one-type grids run on k_march2)
+    if (single) return launch_sel<true, 0>(h, a, step, rot, vm, lean, write_g);
     return launch_sel<false, 0>(h, a, step, rot, vm, false, write_g);
 }
 
@@ -965,12 +944,8 @@ int sg_set_tile_rows(mm_handle *h, int rows) {  // warps per block
     return sg_retile(h, 0);
 }
 
-int sg_set_rpt(mm_handle *h, int rpt) {  // node rows per thread of k_march2
-    SGrid &g = h->sg;
-    if (h->model == MM_MODEL_DEFAULT) return rpt == 1 ? MM_OK : MM_ERR_INVALID;
-    if (!sg_march2_config_ok(rpt, g.tile_rows)) return MM_ERR_INVALID;
-    g.rpt = rpt;
-    return sg_retile(h, 0);
+int sg_set_rpt(mm_handle *h, int rpt) {  // node rows per thread of k_march2: fixed per model in the product library
+    return rpt == h->sg.rpt ? MM_OK : MM_ERR_INVALID;
 }
 
 int sg_set_march2(mm_handle *h, int on) {

@@ -85,14 +85,12 @@ struct SGrid {
     // fast path (mm_march2.cuh): one type, one state, uniform node mass, tensor maps available
     int march2 = 0;                 // the handle's launches go to k_march2
     int march2_wanted = 1;          // option "march2": 0 keeps everything on k_march
-    int unroll = 1;                 // planes per trip of k_march2's steady loop (1 / 2)
     int wrap_on_load = -1;          // k_march2 takes the x / y periodic images on load instead of from ghost nodes; -1 = decide
                                     // from the decomposition (sg_retile: slabs yes, a single GPU no - measured in profiles/r02)
     int wrap_wanted = -1;           // option "wrap_on_load"
     int tail_in_kernel = 0;         // the tail runs inside the marching launch (last block) instead of as its own launch
     int tail_wanted = 1;            // option "tail": 0 keeps the reduction / exchange / scalar algebra in their own launches
     int rpt = 2;                    // node rows per thread of k_march2 (tile = 32 x rpt * tile_rows nodes)
-    int pin_step = 0, pin_force = 3;  // rows of Bq held in per-thread registers (k_march2 PIN) by the STEP / FORCE launches
     int tma_rows = 0;               // box rows the tensor maps were encoded for
     int mass_uniform = 1;           // all node masses equal (checked when the masses are uploaded)
     double mass = 1.0;

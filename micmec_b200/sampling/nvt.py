@@ -94,13 +94,28 @@ class BerendsenThermostat(_HostThermostat):
 
 class LangevinThermostat(_HostThermostat):
     """Half-step Ornstein-Uhlenbeck velocity update before and after the Verlet step (nvt.py:165-218); this is the
-    thermostat ``simulations/md.py`` uses."""
+    thermostat ``simulations/md.py`` uses.
+
+    Two implementations behind the reference's constructor:
+
+    * host-driven (the reference's arithmetic on NumPy arrays, noise from the legacy global NumPy generator in the
+      reference's call order): a seeded run reproduces the reference's trajectory; every force evaluation crosses PCIe;
+    * device-resident (``device=True``; the default from 4096 nodes on, when this is the only Verlet hook): the update
+      runs in ``k_langevin`` inside ``mm_md_run`` with a counter-based generator (Philox4x32-10) seeded from the NumPy
+      generator at initialisation.  Same distribution, different stream: parity with the reference is statistical.
+    """
 
     name = "Langevin"
     kind = "stochastic"
+    device_threshold = 4096  # nodes
 
-    def __init__(self, temp, start=0, timecon=100 * femtosecond):
+    def __init__(self, temp, start=0, timecon=100 * femtosecond, device=None):
         _HostThermostat.__init__(self, temp, start, 1, timecon)
+        self.device = device
+        self.seed = None
+
+    def wants_device(self, nnodes):
+        return bool(self.device) if self.device is not None else nnodes >= self.device_threshold
 
     def thermo(self, iterative):
         damp = np.exp(-iterative.timestep / self.timecon / 2)

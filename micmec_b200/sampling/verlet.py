@@ -171,7 +171,7 @@ class VerletIntegrator(Iterative):
     def _native_setup(self):
         """Return (part, thermostat, barostat) when the step can stay on the device, else None."""
         from ..pes.mmff import ForcePartMechanical
-        from .nvt import NHCThermostat
+        from .nvt import NHCThermostat, LangevinThermostat
         from .npt import MTKBarostat, TBCombination
 
         parts = getattr(self.mmf, "parts", None)
@@ -182,7 +182,11 @@ class VerletIntegrator(Iterative):
         if len(vhooks) > 1:
             return None
         for hook in vhooks:
-            if not hook.native:  # Langevin / Berendsen / ... hooks, an MTK barostat with its own chain, user hooks
+            if isinstance(hook, LangevinThermostat) and hook.start == 0 and getattr(parts[0], "slab", None) is None \
+                    and hook.wants_device(self.pos.shape[0]):
+                thermo = hook  # device-resident Langevin thermostat (k_langevin)
+                continue
+            if not hook.native:  # Berendsen / CSVR / ... hooks, an MTK barostat with its own chain, user hooks
                 return None
             if isinstance(hook, TBCombination):
                 thermo, baro = hook.thermostat, hook.barostat
@@ -192,7 +196,7 @@ class VerletIntegrator(Iterative):
                 baro = hook
             else:
                 return None
-        if thermo is not None and thermo.chain.length > _lib.MM_MAX_CHAIN:
+        if thermo is not None and hasattr(thermo, "chain") and thermo.chain.length > _lib.MM_MAX_CHAIN:
             return None
         return parts[0], thermo, baro
 
@@ -214,6 +218,15 @@ class VerletIntegrator(Iterative):
         desc.timestep = self.timestep
         desc.ndof = float(self.ndof)
         desc.time0, desc.counter0 = float(self.time), int(self.counter)
+        self._langevin = None
+        if thermo is not None and not hasattr(thermo, "chain"):  # LangevinThermostat in device mode
+            self._langevin, thermo = thermo, None
+            self._thermo = None
+            if self._langevin.seed is None:  # from the legacy global generator: np.random.seed(k) makes the run reproducible
+                self._langevin.seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + 12345
+            desc.has_langevin = 1
+            desc.langevin_temp, desc.langevin_timecon = self._langevin.temp, self._langevin.timecon
+            desc.langevin_seed = self._langevin.seed & (2 ** 64 - 1)
         if thermo is not None:
             desc.has_thermo, desc.chain_length = 1, thermo.chain.length
             desc.thermo_temp, desc.thermo_timecon = thermo.chain.temp, thermo.chain.timecon
@@ -288,6 +301,8 @@ class VerletIntegrator(Iterative):
         for hook in self._verlet_hooks():
             if hook.name == "TBCombination":
                 hook.econs_correction = econs_corr
+        if getattr(self, "_langevin", None) is not None:
+            self._langevin.econs_correction = econs_corr
         self._part.energy = self.mmf.energy = part_energy  # after update_pos / update_rvecs cleared the caches
         self._arrays_fresh = arrays
 
