@@ -25,7 +25,7 @@ S_VTENS, S_PTENS, S_NFORCE, S_CE_N, S_COUNT = 16, 25, 34, 35, 40
 EXPORTS = [
     "mm_create", "mm_destroy", "mm_last_error", "mm_version", "mm_device_ok", "mm_set_pos", "mm_set_rvecs",
     "mm_compute", "mm_get_cell_cache", "mm_launch_count", "mm_device_ptr", "mm_set_stream", "mm_synchronize",
-    "mm_set_option", "mm_get_option", "mm_profile", "mm_batched_eigh", "mm_set_rvecs_batch", "mm_get_replica_results", "mm_comm_unique_id", "mm_comm_init", "mm_comm_destroy", "mm_comm_mode", "mm_domain", "mm_md_create", "mm_md_destroy", "mm_md_init", "mm_md_set_state", "mm_md_run", "mm_md_get_state",
+    "mm_set_option", "mm_get_option", "mm_profile", "mm_batched_eigh", "mm_qn_create", "mm_qn_destroy", "mm_qn_sweep", "mm_qn_get", "mm_set_rvecs_batch", "mm_get_replica_results", "mm_comm_unique_id", "mm_comm_init", "mm_comm_destroy", "mm_comm_mode", "mm_domain", "mm_md_create", "mm_md_destroy", "mm_md_init", "mm_md_set_state", "mm_md_run", "mm_md_get_state",
     "mm_md_scalars",
 ]
 
@@ -121,6 +121,10 @@ def load():
     lib.mm_comm_destroy.argtypes = [vp]
     lib.mm_comm_mode.argtypes = [vp]
     lib.mm_batched_eigh.argtypes = [i32, i64, i32, vp, i32, vp, vp, ctypes.POINTER(i32)]
+    lib.mm_qn_create.argtypes = [vp, vp, dbl, dbl, dbl, dbl, dbl, ctypes.POINTER(vp)]
+    lib.mm_qn_destroy.argtypes = [vp]
+    lib.mm_qn_sweep.argtypes = [vp, i32, ctypes.POINTER(i32)]
+    lib.mm_qn_get.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(i64)]
     lib.mm_domain.argtypes = [vp, i32, ctypes.POINTER(dbl), vp]
     lib.mm_md_create.argtypes = [vp, ctypes.POINTER(MDDesc), ctypes.POINTER(vp)]
     lib.mm_md_destroy.argtypes = [vp]

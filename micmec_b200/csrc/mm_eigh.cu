@@ -154,8 +154,11 @@ EIGH_DEVICE int jacobi_eigh(int n, int ld, double *A, double *V, double *cs, int
 }
 
 #ifndef MM_EIGH_HOST
+// mask (may be null): matrices whose entry is zero are skipped (the lockstep optimiser only needs the spectra of the
+// replicas whose Hessian model has just changed)
 __global__ void __launch_bounds__(256) k_batched_eigh(const double *__restrict__ mats, int n, int ld, double *__restrict__ evals,
-                                                      double *__restrict__ evecs, int *__restrict__ sweeps) {
+                                                      double *__restrict__ evecs, int *__restrict__ sweeps, const int *__restrict__ mask) {
+    if (mask && !mask[blockIdx.x]) return;
     extern __shared__ __align__(16) double sm[];
     double *A = sm;
     double *V = A + (size_t)n * ld;
@@ -178,6 +181,23 @@ __global__ void __launch_bounds__(256) k_batched_eigh(const double *__restrict__
 }  // namespace mm
 
 #ifndef MM_EIGH_HOST
+namespace mm {
+// device arrays in, device arrays out, on the caller's stream (mm_qn.cu)
+int eigh_launch_device(int device, int64_t batch, int n, const double *d_mats, double *d_evals, double *d_evecs, int *d_sweeps,
+                       const int *d_mask, cudaStream_t stream) {
+    const int ld = (n & 1) ? n : n + 1;
+    const size_t smem = sizeof(double) * (2 * (size_t)n * ld + (kEighMaxN + 2) + 2 * 256) + sizeof(int) * (kEighMaxN + 2);
+    static bool configured[64] = {false};
+    if (!configured[device & 63]) {
+        MM_CUDA(cudaFuncSetAttribute(k_batched_eigh, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured[device & 63] = true;
+    }
+    k_batched_eigh<<<(unsigned)batch, 256, smem, stream>>>(d_mats, n, ld, d_evals, d_evecs, d_sweeps, d_mask);
+    MM_CUDA(cudaGetLastError());
+    return MM_OK;
+}
+}  // namespace mm
+
 extern "C" int mm_batched_eigh(int device, int64_t batch, int32_t n, const double *mats, int where, double *evals, double *evecs,
                                int32_t *max_sweeps_out) {
     using namespace mm;
@@ -207,7 +227,7 @@ extern "C" int mm_batched_eigh(int device, int64_t batch, int32_t n, const doubl
         d_v = own + nmat;
         d_w = own + 2 * nmat;
     }
-    k_batched_eigh<<<(unsigned)batch, 256, smem, stream>>>(d_m, n, ld, d_w, d_v, d_sweeps);
+    k_batched_eigh<<<(unsigned)batch, 256, smem, stream>>>(d_m, n, ld, d_w, d_v, d_sweeps, nullptr);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && where == MM_HOST) {
         err = cudaMemcpyAsync(evals, d_w, sizeof(double) * nval, cudaMemcpyDeviceToHost, stream);

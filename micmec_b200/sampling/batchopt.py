@@ -12,7 +12,7 @@ own share (``shard``).
 """
 import numpy as np
 
-__all__ = ["ReplicaQNOptimizer", "solve_trust_radius_batch", "shard"]
+__all__ = ["ReplicaQNOptimizer", "DeviceReplicaQNOptimizer", "solve_trust_radius_batch", "shard"]
 
 _STRAIN_SLOTS = [(0, 0), (1, 1), (2, 2), (1, 2), (2, 0), (0, 1)]  # dof.py:522-531
 
@@ -362,3 +362,74 @@ class ReplicaQNOptimizer(object):
     @property
     def rvecs(self):
         return np.array(self._geometry(self.x)[1])
+
+
+class DeviceReplicaQNOptimizer(object):
+    """The same lockstep optimiser for Cartesian degrees of freedom with EVERYTHING on the device (``csrc/mm_qn.cu``):
+    Hessian models, spectra, ridge search, accept / shrink and convergence state stay in HBM; the host reads one counter
+    per call of ``mm_qn_sweep``.  ``ReplicaQNOptimizer`` (above) moves two [R, n, n] arrays over PCIe per sweep and runs
+    the trust-radius algebra in NumPy; it remains the implementation for the cell degrees of freedom (``dof="strain"``).
+
+    Same state machine, thresholds and attributes as ``ReplicaQNOptimizer(dof="cartesian")``.
+    """
+
+    def __init__(self, batch, pos0, rvecs0, gpos_rms=1e-5, dpos_rms=1e-3, trust_radius=1.0, small_radius=1e-5,
+                 too_small_radius=1e-10):
+        import ctypes
+
+        from .. import _lib
+
+        self._lib_mod, self._ctypes = _lib, ctypes
+        self._lib = _lib.load()
+        self.batch = batch
+        pos0 = np.ascontiguousarray(pos0, dtype=float)
+        self.nrep, self.nnodes = pos0.shape[0], pos0.shape[1]
+        self.rvecs0 = np.ascontiguousarray(rvecs0, dtype=float).reshape(self.nrep, 3, 3)
+        self.ndof = 3 * self.nnodes
+        _lib.check(self._lib.mm_set_rvecs_batch(batch._handle, _lib.ptr(self.rvecs0.reshape(self.nrep, 9).copy())))
+        self._q = ctypes.c_void_p()
+        _lib.check(self._lib.mm_qn_create(batch._handle, _lib.ptr(pos0), gpos_rms, dpos_rms, trust_radius, small_radius,
+                                          too_small_radius, ctypes.byref(self._q)))
+        self.nlive = self.nrep
+
+    def __del__(self):
+        q = getattr(self, "_q", None)
+        if q is not None and q.value:
+            self._lib.mm_qn_destroy(q)
+            self._q = None
+
+    def run(self, max_sweeps=1000, check_every=4):
+        """Sweep until every replica has converged or failed; returns the number of sweeps used."""
+        done = 0
+        live = self._ctypes.c_int32(self.nrep)
+        while done < max_sweeps and self.nlive > 0:
+            k = min(check_every, max_sweeps - done)
+            self._lib_mod.check(self._lib.mm_qn_sweep(self._q, k, self._ctypes.byref(live)))
+            done += k
+            self.nlive = int(live.value)
+        return done
+
+    def _fetch(self):
+        lib, ptr = self._lib_mod, self._lib_mod.ptr
+        x, g = np.zeros((self.nrep, self.ndof)), np.zeros((self.nrep, self.ndof))
+        f, radius, conv_val = np.zeros(self.nrep), np.zeros(self.nrep), np.zeros(self.nrep)
+        ints = [np.zeros(self.nrep, dtype=np.int32) for _ in range(4)]
+        evals = self._ctypes.c_int64()
+        lib.check(self._lib.mm_qn_get(self._q, ptr(x), ptr(f), ptr(g), ptr(radius), ptr(conv_val), ptr(ints[0]), ptr(ints[1]),
+                                      ptr(ints[2]), ptr(ints[3]), self._ctypes.byref(evals)))
+        return dict(x=x, f=f, g=g, trust_radius=radius, conv_val=conv_val, iterations=ints[0].astype(np.int64),
+                    converged=ints[1].astype(bool), failed=ints[2].astype(bool), conv_count=ints[3].astype(np.int64),
+                    evaluations=int(evals.value))
+
+    def __getattr__(self, name):
+        if name in ("x", "f", "g", "trust_radius", "conv_val", "iterations", "converged", "failed", "conv_count", "evaluations"):
+            return self._fetch()[name]
+        raise AttributeError(name)
+
+    @property
+    def pos(self):
+        return self.x.reshape(self.nrep, self.nnodes, 3)
+
+    @property
+    def rvecs(self):
+        return self.rvecs0

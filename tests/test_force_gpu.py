@@ -325,3 +325,67 @@ def test_replica_batch_matches_per_system_oracle(model):
         check_against(e[rep], g[rep], v[rep], eo, go, vo, gio.virial_noise(gc, vc))
     e2, g2, v2 = batch.compute(np.array(pos), np.array(rvecs), gpos=False)
     assert g2 is None and np.array_equal(e2, e) and np.array_equal(v2, v)
+
+
+def open_grid_system(shape, type_params, hollow=()):
+    """Finite (non-periodic) grid of one cell type, conventions of micmec/utils.py:164-263 with pbc = [False] * 3: nodes
+    (nx+1)(ny+1)(nz+1) in C order (only those touched by a cell), cells in C order, -1 for a missing neighbour cell."""
+    from micmec_b200.system import System
+
+    nx, ny, nz = shape
+    grid = np.ones(shape, dtype=np.int64)
+    for idx in hollow:
+        grid[idx] = 0
+    offsets = np.array([(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1), (1, 1, 1)])
+    node_id, nodes = {}, []
+    for k in range(nx + 1):
+        for l in range(ny + 1):
+            for m in range(nz + 1):
+                touched = any(0 <= k - d[0] < nx and 0 <= l - d[1] < ny and 0 <= m - d[2] < nz and grid[k - d[0], l - d[1], m - d[2]]
+                              for d in offsets)
+                if touched:
+                    node_id[(k, l, m)] = len(nodes)
+                    nodes.append((k, l, m))
+    cells = [tuple(c) for c in np.argwhere(grid != 0)]
+    cell_id = {c: n for n, c in enumerate(cells)}
+    sn = np.array([[node_id[(c[0] + d[0], c[1] + d[1], c[2] + d[2])] for d in offsets] for c in cells], dtype=np.int64)
+    sc = np.array([[cell_id.get((n[0] - d[0], n[1] - d[1], n[2] - d[2]), -1) for d in offsets] for n in nodes], dtype=np.int64)
+    h0 = np.asarray(type_params["cell"], dtype=float).reshape(-1, 3, 3)[0]
+    pos = np.array(nodes, dtype=float) * np.diag(h0)
+    masses = np.array([0.125 * float(type_params["mass"]) * np.sum(row >= 0) for row in sc])
+    params = {"type1/" + key: type_params[key] for key in ("cell", "elasticity", "free_energy", "effective_temp", "mass")}
+    return System(pos, masses, np.zeros((0, 3)), sc, sn, grid=grid, types=np.ones(len(cells), dtype=np.int64), params=params)
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_finite_system_without_periodic_images(model):
+    """pbc = False (mmff.py:262-263: no minimum-image shifts; Domain with nvec = 0, domain.c:23-25).  The reference's own
+    `deformation` cannot evaluate such a system (it indexes rvecs[0] of an empty array, mmff.py:349), so the parity target
+    is the sum of the reference's PER-CELL functions (pinned through the oracle's cell_state) over the cells, gathered in
+    the reference's order - which is exactly what `deformation` would compute with zero shifts."""
+    from micmec_b200.celltypes import TYPE_FCU
+
+    system = open_grid_system((3, 2, 2), TYPE_FCU, hollow=[(1, 1, 1)])
+    assert system.domain.nvec == 0 and system.domain.volume == 0.0
+    rng = np.random.default_rng(12)
+    system.pos[:] = system.pos + 0.4 * rng.standard_normal(system.pos.shape)
+    mmf, part = make_mmf(system, model)
+    assert not part.pbc
+    g, v = np.zeros(system.pos.shape), np.zeros((3, 3))
+    e = mmf.compute(g, v)
+    h0 = np.asarray(TYPE_FCU["cell"]).reshape(-1, 3, 3)[0]
+    C = np.asarray(TYPE_FCU["elasticity"]).reshape(-1, 3, 3, 3, 3)[0]
+    eref, gref, vref = 0.0, np.zeros_like(g), np.zeros((3, 3))
+    for c, verts in enumerate(system.surrounding_nodes):
+        ec, gc = orc.Oracle.cell_state(model, system.pos[verts], h0, C)
+        eref += ec
+        gref[verts] += gc
+        vref += gc.T @ system.pos[verts]
+    assert abs(e - eref) <= ETOL * abs(eref)
+    assert gio.rel_rms(g, gref) <= GTOL
+    assert gio.rel_rms(v, vref) <= 1e-8
+    assert abs(g.sum(axis=0)).max() <= 1e-12 * np.abs(g).max()  # a free cluster feels no net force
+    # and the oracle's whole-system path agrees with zero shifts
+    oracle = orc.Oracle(system, model=model, nthreads=2)
+    eo, go, _ = oracle.compute(system.pos, system.domain.rvecs, gpos=True, vtens=False)
+    assert abs(e - eo) <= ETOL * abs(eo) and gio.rel_rms(g, go) <= GTOL
