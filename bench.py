@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--tail", type=int, default=-1, help="tuning: 0 = reduction / exchange / scalar algebra in their own launches")
     ap.add_argument("--march2", type=int, default=-1, help="tuning: 0 = keep the general kernel k_march for the one-type grids too")
     ap.add_argument("--generic", action="store_true", help="force the indexed-topology kernels (no structured path)")
+    ap.add_argument("--config5", type=int, default=0, metavar="R",
+                    help="BASELINE.json configs[4] instead of the MD step: geometry optimisation of R perturbed 27-node "
+                         "replicas of the 3x3x3 defect configurations (device-resident lockstep QN), sharded over the GPUs")
     return ap.parse_args()
 
 
@@ -221,6 +224,67 @@ def workload_config(args, world, comm_mode=None, tiling=None):
     }
 
 
+def run_config5(args, rank, world, local_rank):
+    """configs[4]: R = args.config5 replicas (3 defect topologies x perturbations of a 27-node 3x3x3 grid: the type maps of
+    data/3x3x3_conf{0,3,9}_micmec.chk are not shipped to the GPU box, so the defects are drawn here - 2 types per system as
+    in the reference's fixtures), Cartesian geometry optimisation to gpos_rms 1e-7 / dpos_rms 1e-5, replicas only: every
+    rank optimises its contiguous share, no communication."""
+    import torch
+    import torch.distributed as dist
+    from micmec_b200.system import System
+    from micmec_b200.celltypes import TYPE_FCU, TYPE_TEST
+    from micmec_b200.replicas import ReplicaBatch
+    from micmec_b200.sampling.batchopt import DeviceReplicaQNOptimizer, shard
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    rng = np.random.default_rng(5)
+    base = System.periodic_grid((3, 3, 3), TYPE_FCU, explicit=True)
+    params = dict(base.params)
+    for key in ("cell", "elasticity", "free_energy", "effective_temp", "mass"):
+        params["type2/" + key] = TYPE_FCU[key] if key in ("cell", "mass") else TYPE_TEST[key] if key == "elasticity" else TYPE_FCU[key]
+    topologies = [np.where(rng.random(27) < 0.15, 2, 1) for _ in range(10)]  # conf0..conf9: a few softer defect cells each
+    systems = []
+    for r in range(args.config5):
+        types = topologies[r % 10]
+        s = System(base.pos + 0.5 * rng.standard_normal(base.pos.shape), base.masses, np.array(base.domain.rvecs), base.surrounding_cells,
+                   base.surrounding_nodes, grid=types.reshape(3, 3, 3), types=types, params=params)
+        systems.append(s)
+    mine = shard(systems, rank, world)
+    pos0 = np.stack([s.pos for s in mine])
+    rvecs0 = np.stack([np.array(s.domain.rvecs) for s in mine])
+    batch = ReplicaBatch(mine, device=local_rank)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    opt = DeviceReplicaQNOptimizer(batch, pos0, rvecs0, gpos_rms=1e-7, dpos_rms=1e-5)
+    sweeps = opt.run(2000)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st = opt._fetch()
+    stats = torch.tensor([dt, float(st["converged"].sum()), float(st["failed"].sum()), float(sweeps)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        tmax = stats.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        dt, sweeps = float(tmax[0]), int(tmax[3])
+    if rank == 0:
+        print(json.dumps({
+            "metric": "geometry optimisations/s (config 5: replicas x lockstep QN, fp64)", "value": args.config5 / dt, "unit": "replicas/s",
+            "n_gpus": world, "steps": sweeps, "warmup": 0, "ms_per_step": 1e3 * dt / max(sweeps, 1), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ensemble of %d perturbed 27-node 3x3x3 defect configurations, Cartesian geometry optimisation "
+                                   "(QNOptimizer semantics), replicas only" % args.config5,
+                       "replicas_per_gpu": len(mine), "sweeps": sweeps, "kernels": "mm_qn (k_qn_refresh, k_batched_eigh, k_qn_step, k_cells + k_gather, k_qn_accept)"},
+            "check": {"converged": int(stats[1]), "failed": int(stats[2]), "mean_iterations": float(st["iterations"].mean()),
+                      "mean_energy": float(st["f"].mean())},
+            "gpu_launches": int(batch.launches), "wall_s": dt}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -228,6 +292,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.config5:
+        return run_config5(args, rank, world, local_rank)
 
     import torch
     import torch.distributed as dist
