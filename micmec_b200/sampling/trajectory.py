@@ -18,7 +18,7 @@ import os
 
 import numpy as np
 
-__all__ = ["HDF5Writer", "XYZWriter", "RawWriter", "load_raw"]
+__all__ = ["HDF5Writer", "XYZWriter", "RawWriter", "DeviceRawWriter", "load_raw"]
 
 
 class BaseHDF5Writer(Hook):
@@ -119,6 +119,113 @@ class RawWriter(Hook):
         with open(tmp, "w") as handle:
             json.dump(self.meta, handle, default=lambda o: o.decode() if isinstance(o, bytes) else str(o))
         os.replace(tmp, os.path.join(self.directory, "meta.json"))  # a crash never leaves a half-written index
+
+
+class DeviceRawWriter(Hook):
+    """Streaming writer for the device-resident integrator at benchmark sizes (the reference's
+    ``HDF5Writer`` copies the full ``pos`` array on every call, trajectory.py:31-85).
+
+    Same files as ``RawWriter`` (``load_raw`` reads them), but the frame never passes through the integrator's host
+    mirrors: ``mm_md_get_state`` exports positions (and velocities / gradients on request) straight from the device
+    layout into one of two pinned host buffers, and a background thread appends that buffer to ``<key>.bin`` while the
+    integrator is already running the next steps.  The integrator does not refresh ``iterative.pos / vel / gpos`` for
+    this hook (``wants_arrays = False``): a 256^3 frame costs one 403 MB device-to-host copy per field and nothing else
+    on the critical path.  Scalars (``time``, ``epot``, ``ekin``, ``temp``, ``econs``, ``counter``) go to ``scalars.bin``.
+    """
+
+    wants_arrays = False
+    SCALARS = ("counter", "time", "epot", "ekin", "temp", "etot", "econs", "press", "volume")
+
+    def __init__(self, directory, fields=("pos",), start=0, step=1):
+        import queue
+        import threading
+
+        if not set(fields) <= {"pos", "vel", "gpos"}:
+            raise ValueError("DeviceRawWriter writes pos, vel and / or gpos")
+        self.directory, self.fields = directory, tuple(fields)
+        self.meta = None
+        self._buffers, self._turn = None, 0
+        self._queue = queue.Queue()
+        self._free = [threading.Semaphore(1), threading.Semaphore(1)]
+        self._thread = None
+        self._error = None
+        Hook.__init__(self, start, step)
+
+    @staticmethod
+    def _pinned(shape):
+        try:  # pinned memory makes the device-to-host copy asynchronous-capable and twice as fast; torch is plumbing only
+            import torch
+
+            tensor = torch.empty(shape, dtype=torch.float64).pin_memory()
+            return tensor.numpy(), tensor
+        except Exception:
+            return np.empty(shape), None
+
+    def _writer_loop(self):
+        while True:
+            job = self._queue.get()
+            if job is None:
+                return
+            slot, nframes, scal = job
+            try:
+                for key in self.fields:
+                    with open(os.path.join(self.directory, key + ".bin"), "ab") as handle:
+                        self._buffers[slot][key][0].tofile(handle)
+                with open(os.path.join(self.directory, "scalars.bin"), "ab") as handle:
+                    np.asarray(scal, dtype=float).tofile(handle)
+                self.meta["frames"] = nframes
+                tmp = os.path.join(self.directory, "meta.json.tmp")
+                with open(tmp, "w") as handle:
+                    json.dump(self.meta, handle)
+                os.replace(tmp, os.path.join(self.directory, "meta.json"))
+            except Exception as exc:  # surfaced by the next call / close()
+                self._error = exc
+            finally:
+                self._free[slot].release()
+
+    def _open(self, iterative):
+        import threading
+
+        os.makedirs(self.directory, exist_ok=True)
+        shape = tuple(iterative.pos.shape)
+        self.meta = {"frames": 0, "attrs": {"scalars": list(self.SCALARS)},
+                     "items": {key: {"shape": list(shape), "dtype": "<f8"} for key in self.fields}}
+        self.meta["items"]["scalars"] = {"shape": [len(self.SCALARS)], "dtype": "<f8"}
+        for key in list(self.fields) + ["scalars"]:
+            open(os.path.join(self.directory, key + ".bin"), "wb").close()
+        np.save(os.path.join(self.directory, "system_masses.npy"), np.asarray(iterative.mmf.system.masses))
+        self._buffers = [{key: self._pinned(shape) for key in self.fields} for _ in range(2)]
+        self._thread = threading.Thread(target=self._writer_loop, daemon=True)
+        self._thread.start()
+        self._count = 0
+
+    def __call__(self, iterative):
+        from .. import _lib
+
+        if self._error is not None:
+            raise self._error
+        if not getattr(iterative, "device_mode", False):
+            raise RuntimeError("DeviceRawWriter needs the device-resident integrator; use RawWriter in host-driven mode")
+        if self.meta is None:
+            self._open(iterative)
+        slot = self._turn
+        self._free[slot].acquire()  # the background thread has finished with this buffer
+        bufs = self._buffers[slot]
+        ptrs = [(_lib.ptr(bufs[key][0]) if key in bufs else None) for key in ("pos", "vel", "gpos")]
+        _lib.check(iterative._lib.mm_md_get_state(iterative._md, ptrs[0], ptrs[1], ptrs[2], _lib.MM_HOST, None, None, None, None))
+        self._count += 1
+        scal = [float(getattr(iterative, name, 0.0) if name != "volume" else iterative.mmf.system.domain.volume) for name in self.SCALARS]
+        self._queue.put((slot, self._count, scal))
+        self._turn ^= 1
+
+    def close(self):
+        """Wait until every frame is on disk."""
+        if self._thread is not None:
+            self._queue.put(None)
+            self._thread.join()
+            self._thread = None
+        if self._error is not None:
+            raise self._error
 
 
 def load_raw(directory, mmap=True):

@@ -312,7 +312,7 @@ class VerletIntegrator(Iterative):
         for k in range(1, limit + 1):
             firing = [hook for hook in conventional if hook.expects_call(self.counter + k)]
             if firing:
-                return k, any(not isinstance(hook, VerletScreenLog) for hook in firing)
+                return k, any(not isinstance(hook, VerletScreenLog) and getattr(hook, "wants_arrays", True) for hook in firing)
         return limit, False
 
     def run(self, nsteps=None):
@@ -345,7 +345,7 @@ class VerletIntegrator(Iterative):
         for hook in self.hooks:
             if isinstance(hook, VerletHook) or not hook.expects_call(self.counter):
                 continue
-            if not state_updated:
+            if not state_updated and getattr(hook, "wants_arrays", True):  # hooks that read iterative.state
                 for item in self.state_list:
                     item.update(self)
                 state_updated = True

@@ -273,3 +273,40 @@ def test_restart_continues_time_and_counter_in_device_mode():
     assert ConsErrStateItem("ekin_m").get_value(verlet) > 0.0
     contribs = EPotContribStateItem().get_value(verlet)
     assert contribs.shape == (1,) and abs(contribs[0] - verlet.epot) <= 1e-12 * abs(verlet.epot)
+
+
+def test_device_raw_writer_streams_frames_without_host_mirrors(tmp_path):
+    """DeviceRawWriter: frames exported from the device layout into pinned buffers and written by a
+    background thread equal what the integrator's host mirrors would have held; the mirrors are not refreshed for it."""
+    from micmec_b200.system import System
+    from micmec_b200.celltypes import TYPE_FCU
+    from micmec_b200.pes.mmff import MicMecForceField, ForcePartMechanical
+    from micmec_b200.sampling.verlet import VerletIntegrator
+    from micmec_b200.sampling.nvt import NHCThermostat
+    from micmec_b200.sampling.trajectory import DeviceRawWriter, RawWriter, load_raw
+    from micmec_b200.units import femtosecond
+
+    def run(writer_cls, directory, **kw):
+        rng = np.random.default_rng(2)
+        system = System.periodic_grid((40, 24, 32), TYPE_FCU, explicit=False)
+        system.pos[:] = system.pos + 0.2 * rng.standard_normal(system.pos.shape)
+        mmf = MicMecForceField(system, [ForcePartMechanical(system, structured=True)])
+        vel0 = 1e-5 * rng.standard_normal(system.pos.shape)
+        writer = writer_cls(str(directory), start=0, step=3, **kw)
+        thermo = NHCThermostat(300.0, timecon=100 * femtosecond, chain_vel0=np.array([1e-4, -2e-4, 5e-5]), chain_pos0=np.zeros(3), restart=True)
+        verlet = VerletIntegrator(mmf, timestep=10 * femtosecond, hooks=[thermo, writer], vel0=vel0)
+        verlet.run(10)
+        if hasattr(writer, "close"):
+            writer.close()
+        return verlet
+
+    a = run(DeviceRawWriter, tmp_path / "dev", fields=("pos", "vel"))
+    b = run(RawWriter, tmp_path / "host", keys=("pos", "vel", "epot", "time"))
+    da, db = load_raw(str(tmp_path / "dev")), load_raw(str(tmp_path / "host"))
+    assert da["pos"].shape == db["pos"].shape == (4, 40 * 24 * 32, 3)  # counters 0, 3, 6, 9
+    assert np.array_equal(np.asarray(da["pos"]), np.asarray(db["pos"]))
+    assert np.array_equal(np.asarray(da["vel"]), np.asarray(db["vel"]))
+    names = da["attrs"]["scalars"]
+    assert np.array_equal(da["scalars"][:, names.index("epot")], np.asarray(db["epot"]))
+    assert np.array_equal(da["scalars"][:, names.index("counter")], [0.0, 3.0, 6.0, 9.0])
+    assert np.array_equal(a.pos, b.pos)  # the final state is synchronised as always
