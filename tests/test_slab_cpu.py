@@ -75,3 +75,39 @@ def test_gather_over_gloo_world_size_2(tmp_path):
 
     mp.spawn(_worker, args=(2, _free_port(), (3, 4, 6), str(tmp_path)), nprocs=2, join=True)
     assert np.load(os.path.join(str(tmp_path), "ok.npy")).all()
+
+
+def test_bench_initial_state_is_identical_for_every_decomposition():
+    """bench.py draws ONE global displacement / velocity field and every rank keeps its z-slab of it, so N = 1, 2, 4 and 8
+    integrate the bit-identical initial state (multi-GPU parity must be visible in the driver's records)."""
+    import bench
+    from micmec_b200.slab import SlabLayout
+
+    grid = 16
+    dpos, vel = bench.global_fields(grid)
+    assert abs(vel.mean(axis=0)).max() < 1e-18 + 1e-12 * abs(vel).max()
+    for world in (2, 4, 8):
+        got_p, got_v = np.zeros_like(dpos), np.zeros_like(vel)
+        for rank in range(world):
+            layout = SlabLayout((grid,) * 3, rank, world)
+            ids = layout.global_ids()
+            d2, v2 = bench.global_fields(grid)  # what that rank would draw
+            got_p[ids], got_v[ids] = d2[ids], v2[ids]
+        assert np.array_equal(got_p, dpos) and np.array_equal(got_v, vel)
+
+
+def test_oracle_grid_builder_matches_the_package_generator():
+    """oracle.periodic_grid_system (NumPy only, used by the CPU arm of bench.py) against System.periodic_grid and the
+    reference-derived image table, including 2-wide axes."""
+    from oracle import oracle as orc
+    from micmec_b200.celltypes import TYPE_FCU
+    from micmec_b200.system import System
+
+    for shape in [(4, 3, 5), (2, 2, 2), (3, 2, 4)]:
+        arrays, pos, masses, rvecs = orc.periodic_grid_system(shape, TYPE_FCU)
+        system = System.periodic_grid(shape, TYPE_FCU, explicit=True)
+        assert np.array_equal(arrays["surrounding_nodes"], system.surrounding_nodes)
+        assert np.array_equal(arrays["surrounding_cells"], system.surrounding_cells)
+        assert np.array_equal(arrays["shift"], orc.cell_shifts(system.grid, system.surrounding_nodes, True))
+        assert np.array_equal(pos, system.pos) and np.array_equal(masses, system.masses)
+        assert np.array_equal(rvecs, np.array(system.domain.rvecs))
