@@ -72,7 +72,7 @@ class MDDesc(ctypes.Structure):
         ("baro_press", ctypes.c_double),
         ("baro_timecon", ctypes.c_double),
         ("has_langevin", ctypes.c_int32),
-        ("langevin_pad", ctypes.c_int32),
+        ("thermo_kind", ctypes.c_int32),
         ("langevin_temp", ctypes.c_double),
         ("langevin_timecon", ctypes.c_double),
         ("langevin_seed", ctypes.c_uint64),

@@ -438,6 +438,7 @@ static int baro_force(mm_md *md, bool snapshot, int &nbc, int &nbn) {
 static int md_step(mm_md *md, bool full, bool own_pre, bool merge_next) {
     mm_handle *h = md->h;
     const bool thermo = md->desc.has_thermo != 0, baro = md->desc.has_baro != 0, lang = md->desc.has_langevin != 0;
+    const unsigned post_thermo = (thermo && md->desc.thermo_kind == 0) ? OP_THERMO : 0u;  // Berendsen acts in "pre" only
     const int gn = grid_for(h, h->nnodes, kNodeThreads);
     int nbc = 0, nbn = 0;
     // ---- "pre" hooks: TBCombination.pre = barostat, then thermostat (npt.py:99-115) ----
@@ -461,7 +462,7 @@ static int md_step(mm_md *md, bool full, bool own_pre, bool merge_next) {
                                                        h->d_gpos, md->d_vel, md->d_masses, md->d_pkin);
     h->launches++;
     // ---- "post" hooks: thermostat, then barostat (npt.py:117-148), then verlet.py:158-166 ----
-    unsigned ops = OP_RESET_MVEL | OP_TAKE_FORCE | OP_TAKE_KIN | (thermo ? OP_THERMO : 0u);
+    unsigned ops = OP_RESET_MVEL | OP_TAKE_FORCE | OP_TAKE_KIN | post_thermo;
     int nbd = 0;
     if (!baro) {
         if (full) {
@@ -525,6 +526,7 @@ static void sg_export(mm_md *md, bool pos, bool vel, double *pos_dst) {
 static int md_step_structured(mm_md *md, bool full, bool own_pre, bool merge_next) {
     mm_handle *h = md->h;
     const bool thermo = md->desc.has_thermo != 0, baro = md->desc.has_baro != 0, lang = md->desc.has_langevin != 0;
+    const unsigned post_thermo = (thermo && md->desc.thermo_kind == 0) ? OP_THERMO : 0u;  // Berendsen acts in "pre" only
     const int nb = h->sg.nblocks;
     const unsigned next_op = !merge_next ? 0u : baro ? OP_NEXT_BARO_A : thermo ? OP_NEXT_THERMO : lang ? OP_LANG_B : 0u;
     if (!full && sg_tail_ok(h) && !lang) {
@@ -536,13 +538,13 @@ static int md_step_structured(mm_md *md, bool full, bool own_pre, bool merge_nex
             if (own_pre) scalar_launch(md, OP_BARO_A, 0, 0, 0);
             t.ops = OP_POS_WRITTEN | OP_TAKE_FORCE | OP_BARO_B | (thermo ? OP_THERMO : 0u);
             sg_force(h, true, 2, false, &t);  // npt.py:683-707: rotate, evaluate, write x and g for the step below
-            t.ops = OP_RESET_MVEL | OP_POS_WRITTEN | OP_TAKE_FORCE | OP_TAKE_KIN | (thermo ? OP_THERMO : 0u) | OP_BARO_A;
+            t.ops = OP_RESET_MVEL | OP_POS_WRITTEN | OP_TAKE_FORCE | OP_TAKE_KIN | post_thermo | OP_BARO_A;
             sg_step(h, false, 2, false, &t);
             t.ops = OP_TAKE_FORCE | OP_BARO_B | OP_ECONS | OP_ADVANCE | OP_PROPS | next_op;
             sg_force(h, false, 1, true, &t);  // npt.py:683-707 again: energy + virial of the rotated geometry
         } else {
             if (thermo && own_pre) scalar_launch(md, OP_THERMO, 0, 0, 0);
-            t.ops = OP_RESET_MVEL | OP_POS_WRITTEN | OP_TAKE_FORCE | OP_TAKE_KIN | (thermo ? OP_THERMO : 0u) | OP_ECONS | OP_ADVANCE |
+            t.ops = OP_RESET_MVEL | OP_POS_WRITTEN | OP_TAKE_FORCE | OP_TAKE_KIN | post_thermo | OP_ECONS | OP_ADVANCE |
                     OP_PROPS | next_op;
             sg_step(h, true, thermo ? 1 : 0, true, &t);
         }
@@ -566,7 +568,7 @@ static int md_step_structured(mm_md *md, bool full, bool own_pre, bool merge_nex
     }
     // without a barostat the gradient written here feeds the next step's first kick
     sg_step(h, !baro, baro ? 2 : (thermo ? 1 : 0), !full);
-    unsigned ops = OP_RESET_MVEL | OP_POS_WRITTEN | OP_TAKE_FORCE | OP_TAKE_KIN | (thermo ? OP_THERMO : 0u);
+    unsigned ops = OP_RESET_MVEL | OP_POS_WRITTEN | OP_TAKE_FORCE | OP_TAKE_KIN | post_thermo;
     int nbd = 0;
     if (!baro) {
         sg_halo(h, true, true, true);  // rv_stored is unchanged without a barostat: safe before the scalar kernel
@@ -628,7 +630,11 @@ int mm_md_create(mm_handle *h, const mm_md_desc *desc, mm_md **out) {
         return MM_ERR_INVALID;
     }
     *out = nullptr;
-    if (desc->has_thermo && (desc->chain_length < 1 || desc->chain_length > MM_MAX_CHAIN)) {
+    if (desc->has_thermo && desc->thermo_kind == 1 && desc->has_baro) {
+        set_error("mm_md_create: the device Berendsen thermostat runs without a barostat");
+        return MM_ERR_INVALID;
+    }
+    if (desc->has_thermo && desc->thermo_kind == 0 && (desc->chain_length < 1 || desc->chain_length > MM_MAX_CHAIN)) {
         set_error("mm_md_create: unsupported Nose-Hoover chain length");
         return MM_ERR_INVALID;
     }
@@ -712,6 +718,7 @@ int mm_md_init(mm_md *md, const double *pos, const double *vel, const double *ma
         s.ch_vel[k] = chain_vel ? chain_vel[k] : 0.0;
     }
     s.has_langevin = d.has_langevin;
+    s.thermo_kind = d.has_thermo ? d.thermo_kind : 0;
     s.lg_temp = d.langevin_temp;
     s.lg_timecon = d.langevin_timecon;
     s.lg_seed = d.langevin_seed;

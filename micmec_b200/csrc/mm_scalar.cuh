@@ -31,7 +31,7 @@ struct MDState {
     double Rpos[9];  // to be applied by k_apply_pos
     // structured path: positions stay in the frame of their last write; x_true = (x_stored + shifts(rv_stored)).Rpend
     double Rpend[9], rv_stored[9];
-    // Nose-Hoover chain
+    // Nose-Hoover chain (thermo_kind 0) or Berendsen weak coupling (thermo_kind 1: ch_temp, ch_timecon and be_corr only)
     int has_thermo, chain_len;
     double ch_temp, ch_timecon;
     double ch_pos[MM_MAX_CHAIN], ch_vel[MM_MAX_CHAIN], ch_mass[MM_MAX_CHAIN];
@@ -44,7 +44,8 @@ struct MDState {
     long long ce_n;
     double ce_ekin_m, ce_ekin_s, ce_econs_m, ce_econs_s;
     // Langevin thermostat (nvt.py:165-218): accumulated econs_correction = sum of (ekin before - ekin after) of every call
-    int has_langevin, lg_pad;
+    int has_langevin, thermo_kind;
+    double be_corr;  // Berendsen: accumulated econs_correction (nvt.py:153-162)
     double lg_temp, lg_timecon, lg_corr;
     unsigned long long lg_seed;
     // properties (verlet.py:171-190)
@@ -196,6 +197,15 @@ static __device__ void chain_bead(MDState &s, int k, double ekin, bool has_g1, d
 
 // NHChain.__call__ (nvt.py:410-451): the velocity scaling goes into the pending matrix and the moments
 static __device__ void thermo_call(MDState &s) {
+    if (s.thermo_kind == 1) {  // BerendsenThermostat.pre (nvt.py:146-162): one global velocity scale, deferred like the chain's
+        const double temp_now = 2.0 * s.ekin / (s.boltzmann * s.ndof);
+        const double scale = sqrt(1.0 + s.timestep / s.ch_timecon * (s.ch_temp / temp_now - 1.0));
+        for (int i = 0; i < 9; i++) s.Mvel[i] *= scale;
+        for (int i = 0; i < 6; i++) s.mvv[i] *= scale * scale;
+        s.be_corr += (1.0 - scale * scale) * s.ekin;
+        s.ekin *= scale * scale;
+        return;
+    }
     const bool has_g1 = s.has_baro != 0;  // TBCombination.pre/post, npt.py:107-113, 118-125
     const double g1 = has_g1 ? 2.0 * ekin_baro(s) - s.baro_ndof * s.b_temp * s.boltzmann : 0.0;  // npt.py:738-746
     double ekin = s.ekin;
@@ -284,7 +294,8 @@ static __device__ void baro_b(MDState &s) {
 static __device__ void econs_update(MDState &s) {
     double corr = 0.0;
     const double kb = s.boltzmann;
-    if (s.has_thermo) {  // nvt.py:453-458
+    if (s.has_thermo && s.thermo_kind == 1) corr += s.be_corr;
+    if (s.has_thermo && s.thermo_kind == 0) {  // nvt.py:453-458
         const double kt = kb * s.ch_temp;
         double a = 0.0, p = 0.0;
         for (int k = 0; k < s.chain_len; k++) a += s.ch_vel[k] * s.ch_vel[k] * s.ch_mass[k];
@@ -357,7 +368,7 @@ static __device__ __noinline__ void scalar_ops(MDState &s, double *rvecs_dev, St
     if (ops & OP_SETUP) {  // nvt.py:393-400, npt.py:591-596, verlet.py:131-132, sampling/utils.py:340-343
         if ((s.has_thermo || s.has_baro) && s.ndof <= 0.0) s.ndof = n3 - 3.0;
         if (s.ndof <= 0.0) s.ndof = n3;
-        if (s.has_thermo) {
+        if (s.has_thermo && s.thermo_kind == 0) {
             const double afreq = 2.0 * M_PI / s.ch_timecon;
             for (int k = 0; k < s.chain_len; k++) s.ch_mass[k] = s.boltzmann * s.ch_temp / (afreq * afreq);
             s.ch_mass[0] *= s.ndof;

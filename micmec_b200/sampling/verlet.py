@@ -171,7 +171,7 @@ class VerletIntegrator(Iterative):
     def _native_setup(self):
         """Return (part, thermostat, barostat) when the step can stay on the device, else None."""
         from ..pes.mmff import ForcePartMechanical
-        from .nvt import NHCThermostat, LangevinThermostat
+        from .nvt import NHCThermostat, LangevinThermostat, BerendsenThermostat
         from .npt import MTKBarostat, TBCombination
 
         parts = getattr(self.mmf, "parts", None)
@@ -185,6 +185,9 @@ class VerletIntegrator(Iterative):
             if isinstance(hook, LangevinThermostat) and hook.start == 0 and getattr(parts[0], "slab", None) is None \
                     and hook.wants_device(self.pos.shape[0]):
                 thermo = hook  # device-resident Langevin thermostat (k_langevin)
+                continue
+            if isinstance(hook, BerendsenThermostat) and hook.start == 0 and getattr(parts[0], "slab", None) is None:
+                thermo = hook  # weak coupling: one deterministic velocity scale per step, computed by the scalar kernel
                 continue
             if not hook.native:  # Berendsen / CSVR / ... hooks, an MTK barostat with its own chain, user hooks
                 return None
@@ -218,7 +221,12 @@ class VerletIntegrator(Iterative):
         desc.timestep = self.timestep
         desc.ndof = float(self.ndof)
         desc.time0, desc.counter0 = float(self.time), int(self.counter)
-        self._langevin = None
+        self._langevin = self._berendsen = None
+        if thermo is not None and thermo.name == "Berendsen":
+            self._berendsen, thermo = thermo, None
+            self._thermo = None
+            desc.has_thermo, desc.thermo_kind, desc.chain_length = 1, 1, 0
+            desc.thermo_temp, desc.thermo_timecon = self._berendsen.temp, self._berendsen.timecon
         if thermo is not None and not hasattr(thermo, "chain"):  # LangevinThermostat in device mode
             self._langevin, thermo = thermo, None
             self._thermo = None
@@ -301,8 +309,9 @@ class VerletIntegrator(Iterative):
         for hook in self._verlet_hooks():
             if hook.name == "TBCombination":
                 hook.econs_correction = econs_corr
-        if getattr(self, "_langevin", None) is not None:
-            self._langevin.econs_correction = econs_corr
+        for hook in (getattr(self, "_langevin", None), getattr(self, "_berendsen", None)):
+            if hook is not None:
+                hook.econs_correction = econs_corr
         self._part.energy = self.mmf.energy = part_energy  # after update_pos / update_rvecs cleared the caches
         self._arrays_fresh = arrays
 
