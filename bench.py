@@ -259,7 +259,7 @@ def run_config5(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    opt = DeviceReplicaQNOptimizer(batch, pos0, rvecs0, gpos_rms=1e-7, dpos_rms=1e-5)
+    opt = DeviceReplicaQNOptimizer(batch, pos0, rvecs0, dof="cartesian", gpos_rms=1e-7, dpos_rms=1e-5)
     sweeps = opt.run(2000)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0

@@ -135,18 +135,22 @@ int mm_batched_eigh(int device, int64_t batch, int32_t n, const double *mats, in
                     int32_t *max_sweeps_out);
 
 /* ---- device-resident lockstep quasi-Newton optimiser of a replica batch (config 5) ------------------------------------ */
-/* QNOptimizer over a CartesianDOF (micmec/sampling/opt.py:258-443, dof.py:75-193), one instance per replica of the batch
- * handle `h` (created with nreplicas > 1; per-replica domain vectors set with mm_set_rvecs_batch), all replicas advancing in
- * lockstep: SR1 Hessian models, their spectra (Jacobi), the ridge search of solve_trust_radius, accept / shrink and the
- * convergence criteria run on the device; a sweep costs one batched force evaluation.  pos0 [R][nnodes][3] (host).
- * Thresholds and radii: QNOptimizer(trust_radius, small_radius, too_small_radius), CartesianDOF(gpos_rms, dpos_rms). */
+/* QNOptimizer over a CartesianDOF (kind 0) or a StrainCellDOF (kind 1) - micmec/sampling/opt.py:258-443, dof.py:75-193,
+ * 522-697 - one instance per replica of the batch handle `h` (created with nreplicas > 1; per-replica domain vectors set with
+ * mm_set_rvecs_batch), all replicas advancing in lockstep: SR1 Hessian models, their spectra (Jacobi), the ridge search of
+ * solve_trust_radius, accept / shrink, the DOF mappings and the convergence criteria run on the device; a sweep costs one
+ * batched force evaluation.  x0 [R][ndof] (host): positions (kind 0) or [6 strain variables, fractional coordinates]
+ * (kind 1).  kind 1 also takes rvecs0 [R][9], jac [R][9][6] = d rvecs / d strain and proj [R][9][9], the projector on the
+ * range of jac (dof.py:582-697).  Thresholds and radii: QNOptimizer(trust_radius, small_radius, too_small_radius),
+ * DOF(gpos_rms, dpos_rms, grvecs_rms, drvecs_rms). */
 typedef struct mm_qn mm_qn;
-int mm_qn_create(mm_handle *h, const double *pos0_host, double gpos_rms, double dpos_rms, double trust_radius,
-                 double small_radius, double too_small_radius, mm_qn **out);
+int mm_qn_create(mm_handle *h, int kind, const double *x0_host, const double *rvecs0_host, const double *jac_host,
+                 const double *proj_host, double gpos_rms, double dpos_rms, double grvecs_rms, double drvecs_rms,
+                 double trust_radius, double small_radius, double too_small_radius, mm_qn **out);
 int mm_qn_destroy(mm_qn *q);
 /* nsweeps sweeps; *nlive_out = replicas that have neither converged nor failed (trust radius underflow) yet */
 int mm_qn_sweep(mm_qn *q, int nsweeps, int *nlive_out);
-/* state read-back (host arrays, any may be NULL): x, g [R][3 nnodes]; f, radius, conv_val [R]; int32 [R]: accepted steps,
+/* state read-back (host arrays, any may be NULL): x, g [R][ndof]; f, radius, conv_val [R]; int32 [R]: accepted steps,
  * converged, failed, number of unmet criteria; *evaluations = batched force calls so far */
 int mm_qn_get(mm_qn *q, double *x, double *f, double *g, double *radius, double *conv_val, int32_t *iterations,
               int32_t *converged, int32_t *failed, int32_t *conv_count, int64_t *evaluations);

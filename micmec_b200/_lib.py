@@ -121,7 +121,7 @@ def load():
     lib.mm_comm_destroy.argtypes = [vp]
     lib.mm_comm_mode.argtypes = [vp]
     lib.mm_batched_eigh.argtypes = [i32, i64, i32, vp, i32, vp, vp, ctypes.POINTER(i32)]
-    lib.mm_qn_create.argtypes = [vp, vp, dbl, dbl, dbl, dbl, dbl, ctypes.POINTER(vp)]
+    lib.mm_qn_create.argtypes = [vp, i32, vp, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, dbl, dbl, ctypes.POINTER(vp)]
     lib.mm_qn_destroy.argtypes = [vp]
     lib.mm_qn_sweep.argtypes = [vp, i32, ctypes.POINTER(i32)]
     lib.mm_qn_get.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(i64)]

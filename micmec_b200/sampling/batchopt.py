@@ -365,30 +365,51 @@ class ReplicaQNOptimizer(object):
 
 
 class DeviceReplicaQNOptimizer(object):
-    """The same lockstep optimiser for Cartesian degrees of freedom with EVERYTHING on the device (``csrc/mm_qn.cu``):
-    Hessian models, spectra, ridge search, accept / shrink and convergence state stay in HBM; the host reads one counter
-    per call of ``mm_qn_sweep``.  ``ReplicaQNOptimizer`` (above) moves two [R, n, n] arrays over PCIe per sweep and runs
-    the trust-radius algebra in NumPy; it remains the implementation for the cell degrees of freedom (``dof="strain"``).
+    """The same lockstep optimiser with EVERYTHING on the device (``csrc/mm_qn.cu``): Hessian models, spectra, ridge
+    search, DOF mappings, accept / shrink and convergence state stay in HBM; the host reads one counter per call of
+    ``mm_qn_sweep``.  ``ReplicaQNOptimizer`` (above) moves two [R, n, n] arrays over PCIe per sweep and runs the
+    trust-radius algebra in NumPy.
 
-    Same state machine, thresholds and attributes as ``ReplicaQNOptimizer(dof="cartesian")``.
+    Same state machine, thresholds and attributes as ``ReplicaQNOptimizer`` for ``dof="cartesian"`` and ``dof="strain"``.
     """
 
-    def __init__(self, batch, pos0, rvecs0, gpos_rms=1e-5, dpos_rms=1e-3, trust_radius=1.0, small_radius=1e-5,
-                 too_small_radius=1e-10):
+    def __init__(self, batch, pos0, rvecs0, dof="cartesian", gpos_rms=1e-5, dpos_rms=1e-3, grvecs_rms=1e-5, drvecs_rms=1e-3,
+                 trust_radius=1.0, small_radius=1e-5, too_small_radius=1e-10):
         import ctypes
 
         from .. import _lib
 
+        if dof not in ("cartesian", "strain"):
+            raise ValueError("dof must be 'cartesian' or 'strain'")
         self._lib_mod, self._ctypes = _lib, ctypes
         self._lib = _lib.load()
-        self.batch = batch
+        self.batch, self.kind = batch, dof
         pos0 = np.ascontiguousarray(pos0, dtype=float)
         self.nrep, self.nnodes = pos0.shape[0], pos0.shape[1]
         self.rvecs0 = np.ascontiguousarray(rvecs0, dtype=float).reshape(self.nrep, 3, 3)
-        self.ndof = 3 * self.nnodes
         _lib.check(self._lib.mm_set_rvecs_batch(batch._handle, _lib.ptr(self.rvecs0.reshape(self.nrep, 9).copy())))
+        rv0 = jac = proj = None
+        if dof == "cartesian":
+            x0 = pos0.reshape(self.nrep, -1).copy()
+        else:  # StrainCellDOF (dof.py:522-697), as ReplicaQNOptimizer sets it up
+            frac = np.einsum("rni,rji->rnj", pos0, np.linalg.inv(self.rvecs0).transpose(0, 2, 1))
+            cell0 = np.tile(np.array([1.0, 1.0, 1.0, 0.0, 0.0, 0.0]), (self.nrep, 1))
+            x0 = np.ascontiguousarray(np.concatenate([cell0, frac.reshape(self.nrep, -1)], axis=1))
+            basis = np.zeros((6, 3, 3))
+            for k, (i, j) in enumerate(_STRAIN_SLOTS):
+                if i == j:
+                    basis[k, i, i] = 1.0
+                else:
+                    basis[k, i, j] = basis[k, j, i] = 0.5
+            self._basis = basis
+            jac = np.ascontiguousarray(np.einsum("kij,rjl->rkil", basis, self.rvecs0).reshape(self.nrep, 6, 9).transpose(0, 2, 1))
+            u = np.linalg.svd(jac, full_matrices=False)[0]
+            proj = np.ascontiguousarray(u @ u.transpose(0, 2, 1))
+            rv0 = np.ascontiguousarray(self.rvecs0.reshape(self.nrep, 9))
+        self.ndof = x0.shape[1]
         self._q = ctypes.c_void_p()
-        _lib.check(self._lib.mm_qn_create(batch._handle, _lib.ptr(pos0), gpos_rms, dpos_rms, trust_radius, small_radius,
+        _lib.check(self._lib.mm_qn_create(batch._handle, 0 if dof == "cartesian" else 1, _lib.ptr(x0), _lib.ptr(rv0), _lib.ptr(jac),
+                                          _lib.ptr(proj), gpos_rms, dpos_rms, grvecs_rms, drvecs_rms, trust_radius, small_radius,
                                           too_small_radius, ctypes.byref(self._q)))
         self.nlive = self.nrep
 
@@ -426,10 +447,16 @@ class DeviceReplicaQNOptimizer(object):
             return self._fetch()[name]
         raise AttributeError(name)
 
+    def _geometry(self, x):
+        if self.kind == "cartesian":
+            return x.reshape(self.nrep, self.nnodes, 3), self.rvecs0
+        rvecs = np.einsum("rk,kij->rij", x[:, :6], self._basis) @ self.rvecs0
+        return x[:, 6:].reshape(self.nrep, self.nnodes, 3) @ rvecs, rvecs
+
     @property
     def pos(self):
-        return self.x.reshape(self.nrep, self.nnodes, 3)
+        return self._geometry(self.x)[0]
 
     @property
     def rvecs(self):
-        return self.rvecs0
+        return np.array(self._geometry(self.x)[1])

@@ -69,27 +69,33 @@ def test_batched_eigh_rejects_bad_sizes():
         _eigh(np.zeros((2, 97, 97)), 0, "device")
 
 
-def test_device_resident_optimiser_matches_host_driven_lockstep_run():
-    """mm_qn (SR1 update, spectra, ridge search, accept / shrink, convergence all on the device) against the host-driven
-    lockstep optimiser on the same replica batch: same minima, same discrete outcome, iteration counts within the
-    tolerance the host-driven optimiser has against the oracle-driven one."""
+@pytest.mark.parametrize("kind", ["cartesian", "strain"])
+def test_device_resident_optimiser_matches_host_driven_lockstep_run(kind):
+    """mm_qn (SR1 update, spectra, ridge search, DOF mappings, accept / shrink, convergence all on the device) against the
+    host-driven lockstep optimiser on the same replica batch: same minima, same discrete outcome, iteration counts within
+    the tolerance the host-driven optimiser has against the oracle-driven one."""
     from micmec_b200.replicas import ReplicaBatch
     from micmec_b200.sampling.batchopt import ReplicaQNOptimizer, DeviceReplicaQNOptimizer
 
-    kwargs, args = dict(gpos_rms=1e-7, dpos_rms=1e-5), (["3x3x3_conf0", "3x3x3_conf3", "3x3x3_conf9"], 16, 0.5)
+    if kind == "cartesian":
+        kwargs, args = dict(gpos_rms=1e-7, dpos_rms=1e-5), (["3x3x3_conf0", "3x3x3_conf3", "3x3x3_conf9"], 16, 0.5)
+    else:
+        kwargs = dict(gpos_rms=1e-8, dpos_rms=1e-6, grvecs_rms=1e-8, drvecs_rms=1e-6)
+        args = (["3x3x3_conf0", "3x3x3_conf3", "3x3x3_conf9"], 8, 0.3, 0.02)
     systems = replicas(*args)
     pos0 = np.stack([s.pos for s in systems])
     rvecs0 = np.stack([np.array(s.domain.rvecs) for s in systems])
-    dev = DeviceReplicaQNOptimizer(ReplicaBatch(systems), pos0, rvecs0, **kwargs)
+    dev = DeviceReplicaQNOptimizer(ReplicaBatch(systems), pos0, rvecs0, dof=kind, **kwargs)
     sweeps = dev.run(400)
     assert dev.converged.all() and not dev.failed.any() and sweeps < 400
-    host = ReplicaQNOptimizer(ReplicaBatch(replicas(*args)), pos0, rvecs0, dof="cartesian", **kwargs)
+    host = ReplicaQNOptimizer(ReplicaBatch(replicas(*args)), pos0, rvecs0, dof=kind, **kwargs)
     host.run(400)
     assert host.converged.all()
     f0 = float(host.f_old.max())
     for r in range(len(systems)):
         scale = np.sqrt(np.mean((host.pos[r] - pos0[r]) ** 2))
         assert np.max(np.abs(dev.pos[r] - host.pos[r])) <= 1e-4 * scale, r
+        assert np.max(np.abs(dev.rvecs[r] - host.rvecs[r])) <= 1e-6 * np.sqrt(np.mean(host.rvecs[r] ** 2)), r
         assert abs(dev.f[r] - host.f[r]) <= 1e-8 * f0 + 1e-12, r
         assert abs(int(dev.iterations[r]) - int(host.iterations[r])) <= 6, r
     assert np.all(dev.conv_count == 0) and np.all(dev.conv_val < 1.0)
