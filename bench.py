@@ -10,10 +10,15 @@ step, BASELINE.json configs[3]).  One JSON line is printed by rank 0.
 `value`        device-resident loop (mm_md_run), state already in HBM, CUDA events on the launching stream
 `e2e`          the same step driven through the C ABI with HOST buffers: pinned-host pos+vel uploaded, one step,
                pos+vel+scalars read back, every step
-`roofline`     dominant kernel (the per-cell force kernel): algorithmic bytes / measured launch time vs the measured
-               HBM copy bandwidth in MEASURED_PEAKS.json
+`roofline`     dominant kernel (the fused kick-drift-force-kick launch k_march2<STEP>): algorithmic bytes / measured launch
+               time vs the measured HBM copy bandwidth in MEASURED_PEAKS.json; `fp64` = the same launch against the measured
+               FP64 issue peak, `binding` = whichever roofline is the slower one, `traffic` = DRAM bytes of that kernel
+               from the committed ncu capture (profiles/ncu_traffic.json)
 `cpu_baseline` the CPU oracle port (oracle/micmec_oracle.c, OpenMP) timed on the box's host cores on a bounded sample
-`--impl reference` times that CPU port alone, with all host threads, on the same metric.
+`check`        scalars after the run (identical initial state at every N: they agree across N to ~1e-15) and the drift of
+               the conserved quantity over the timed steps relative to the kinetic energy
+`--impl reference` times that CPU port alone, with all host threads, on the same metric (its input is built with NumPy only).
+`--config5 R`  BASELINE.json configs[4] instead: geometry optimisation of R 27-node replicas, sharded over the GPUs.
 """
 import argparse
 import ctypes

@@ -198,6 +198,9 @@ class DeviceRawWriter(Hook):
         self._thread = threading.Thread(target=self._writer_loop, daemon=True)
         self._thread.start()
         self._count = 0
+        import atexit
+
+        atexit.register(self.close)  # frames still queued when the interpreter exits are written, not dropped
 
     def __call__(self, iterative):
         from .. import _lib
