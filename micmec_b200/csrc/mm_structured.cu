@@ -426,11 +426,11 @@ int sg_retile(mm_handle *h, int chunk_override) {
         g.march2 = 0;
     }
     if (!g.march2 && g.tma_rows != g.tile_rows) sg_encode_maps(h, g.tile_rows);
-    // Periodic images on load + tail launch (no ghost refresh, no hand-over kernel between two marching launches) pay off
-    // when slabs have to synchronise anyway; on one GPU the ghost-fill launch is cheaper than the image copies of the edge
-    // tiles (1.405 vs 1.447 ms per NPT step at 256^3, profiles/r02/g)
-    g.wrap_on_load = g.wrap_wanted >= 0 ? g.wrap_wanted : (h->slab_count > 1 ? 1 : 0);
-    g.tma_ok = g.tma_rows == sg_tile_rows_total(g) ? 1 : 0;
+    // Periodic images on load + tail launch (nothing between two marching launches but one single-block kernel) pay off
+    // when slabs have to synchronise anyway and on small grids, where a step is a handful of short launches; from ~160^3
+    // nodes per GPU on, the ghost-fill launch is cheaper than the image copies of the edge tiles (measured on one GPU,
+    // profiles/r02/z: 64^3 NPT 0.092 vs 0.099 ms, 128^3 0.316 vs 0.337, 160^3 0.460 vs 0.440, 256^3 1.437 vs 1.406)
+    g.wrap_on_load = g.wrap_wanted >= 0 ? g.wrap_wanted : ((h->slab_count > 1 || h->nnodes <= 128 * 128 * 128) ? 1 : 0);
     g.chunk = chunk_override > 0 ? chunk_override : sg_pick_chunk(h);
     dim3 grid;
     const int nb = sg_blocks(h, grid);
