@@ -187,7 +187,8 @@ typedef struct {
      * comes from a counter-based generator (Philox4x32-10 keyed by seed, node id and half-step number): the same node gets
      * the same kick on every GPU and in every kernel layout, but the stream is not NumPy's - parity is statistical. */
     int32_t has_langevin;
-    int32_t thermo_kind;  /* with has_thermo: 0 Nose-Hoover chain, 1 Berendsen weak coupling (nvt.py:110-162; thermo_temp, thermo_timecon) */
+    int32_t thermo_kind;  /* with has_thermo: 0 Nose-Hoover chain, 1 Berendsen weak coupling (nvt.py:110-162), 2 stochastic velocity
+                           * rescaling (CSVR, nvt.py:221-274; noise from langevin_seed) - both use thermo_temp, thermo_timecon */
     double langevin_temp, langevin_timecon;
     uint64_t langevin_seed;
     double time0;      /* VerletIntegrator(time0=...), verlet.py:96: simulation time at initialisation (restarts) */

@@ -68,24 +68,6 @@ constexpr int kNodeThreadsL = 256;
 // xi comes from Philox4x32-10 (Salmon et al., SC'11) keyed by the seed and counted by (reference node id, half-step
 // number, draw): a node gets the same kick wherever a copy of it lives - ghost nodes, halo planes of a z-slab, the AoS
 // arrays of the indexed kernels - so no exchange follows the update, and structured and indexed runs of one seed agree.
-__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned (&out)[4]) {
-#pragma unroll
-    for (int round = 0; round < 10; round++) {
-        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
-        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (unsigned)p1;
-        c3 = (unsigned)p0;
-        c0 = n0;
-        c2 = n2;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    out[0] = c0;
-    out[1] = c1;
-    out[2] = c2;
-    out[3] = c3;
-}
-
 // three standard normal deviates of node `gid` at half-step `phase` (Box-Muller on 64-bit uniforms)
 __device__ __forceinline__ void langevin_noise(unsigned long long seed, long long gid, long long phase, double (&xi)[3]) {
     double z[4];
@@ -630,8 +612,8 @@ int mm_md_create(mm_handle *h, const mm_md_desc *desc, mm_md **out) {
         return MM_ERR_INVALID;
     }
     *out = nullptr;
-    if (desc->has_thermo && desc->thermo_kind == 1 && desc->has_baro) {
-        set_error("mm_md_create: the device Berendsen thermostat runs without a barostat");
+    if (desc->has_thermo && desc->thermo_kind != 0 && (desc->has_baro || desc->thermo_kind < 0 || desc->thermo_kind > 2)) {
+        set_error("mm_md_create: the device Berendsen / CSVR thermostats run without a barostat");
         return MM_ERR_INVALID;
     }
     if (desc->has_thermo && desc->thermo_kind == 0 && (desc->chain_length < 1 || desc->chain_length > MM_MAX_CHAIN)) {
@@ -719,6 +701,7 @@ int mm_md_init(mm_md *md, const double *pos, const double *vel, const double *ma
     }
     s.has_langevin = d.has_langevin;
     s.thermo_kind = d.has_thermo ? d.thermo_kind : 0;
+    if (s.thermo_kind == 2) s.lg_seed = d.langevin_seed;  // the stochastic velocity rescaling draws from the same generator
     s.lg_temp = d.langevin_temp;
     s.lg_timecon = d.langevin_timecon;
     s.lg_seed = d.langevin_seed;

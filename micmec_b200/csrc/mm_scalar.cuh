@@ -72,6 +72,45 @@ enum : unsigned {
     OP_LANG_B = 1u << 16,       // ... and its second half-step (the NEXT step's "pre", merged into the same launch)
 };
 
+// ---- counter-based random numbers (Philox4x32-10, Salmon et al., SC'11): the device-resident stochastic hooks -------------
+static __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned (&out)[4]) {
+#pragma unroll
+    for (int round = 0; round < 10; round++) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (unsigned)p1;
+        c3 = (unsigned)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// two independent standard normal deviates (Box-Muller on 64-bit uniforms) of stream (seed, c0..c3)
+static __device__ __forceinline__ void philox_normal2(unsigned long long seed, unsigned c0, unsigned c1, unsigned c2, unsigned c3, double &z0,
+                                                      double &z1) {
+    unsigned r[4];
+    philox4x32_10(c0, c1, c2, c3, (unsigned)seed, (unsigned)(seed >> 32), r);
+    const double u1 = ((double)(((unsigned long long)r[0] << 32) | r[1]) + 0.5) * 5.421010862427522e-20;  // 2^-64
+    const double u2 = ((double)(((unsigned long long)r[2] << 32) | r[3]) + 0.5) * 5.421010862427522e-20;
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+// one uniform deviate in (0, 1) of stream (seed, c0..c3)
+static __device__ __forceinline__ double philox_uniform(unsigned long long seed, unsigned c0, unsigned c1, unsigned c2, unsigned c3) {
+    unsigned r[4];
+    philox4x32_10(c0, c1, c2, c3, (unsigned)seed, (unsigned)(seed >> 32), r);
+    return ((double)(((unsigned long long)r[0] << 32) | r[1]) + 0.5) * 5.421010862427522e-20;
+}
+
 // ------------------------------------------------------------------------------------------- 3x3 helpers ----
 static __device__ __forceinline__ void mat_mul(const double *a, const double *b, double *c) {  // c = a b (c may alias neither)
     // unrolled: nine independent chains of three - this code runs on ONE thread between two marching launches, its
@@ -206,6 +245,37 @@ static __device__ void thermo_call(MDState &s) {
         s.ekin *= scale * scale;
         return;
     }
+    if (s.thermo_kind == 2) {  // CSVRThermostat.pre (nvt.py:259-271; Bussi, Donadio, Parrinello 2007): one stochastic velocity scale
+        const double c = exp(-s.timestep / s.ch_timecon);
+        const unsigned step = (unsigned)s.counter, step_hi = (unsigned)((unsigned long long)s.counter >> 32);
+        double R, z;
+        philox_normal2(s.lg_seed, step, step_hi, 0x43535652u, 0u, R, z);
+        // S = sum of ndof - 1 squared normal deviates = 2 Gamma((ndof - 1) / 2)  (Marsaglia & Tsang 2000; the reference draws
+        // the ndof - 1 deviates themselves)
+        const double shape = 0.5 * (s.ndof - 1.0), d = shape - 1.0 / 3.0, cc = 1.0 / sqrt(9.0 * d);
+        double S = 2.0 * d;
+        for (unsigned it = 1; it < 1000u; it++) {
+            double x, x2;
+            philox_normal2(s.lg_seed, step, step_hi, 0x43535652u, it, x, x2);
+            double v = 1.0 + cc * x;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            const double u = philox_uniform(s.lg_seed, step, step_hi, 0x43535653u, it);
+            if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) {
+                S = 2.0 * d * v;
+                break;
+            }
+        }
+        const double kin = 0.5 * s.ndof * s.boltzmann * s.ch_temp;
+        const double fact = (1.0 - c) * kin / s.ndof / s.ekin;
+        const double arg = R + sqrt(c / fact);
+        const double alpha = (arg >= 0.0 ? 1.0 : -1.0) * sqrt(c + (S + R * R) * fact + 2.0 * R * sqrt(c * fact));
+        for (int i = 0; i < 9; i++) s.Mvel[i] *= alpha;
+        for (int i = 0; i < 6; i++) s.mvv[i] *= alpha * alpha;
+        s.be_corr += (1.0 - alpha * alpha) * s.ekin;
+        s.ekin *= alpha * alpha;
+        return;
+    }
     const bool has_g1 = s.has_baro != 0;  // TBCombination.pre/post, npt.py:107-113, 118-125
     const double g1 = has_g1 ? 2.0 * ekin_baro(s) - s.baro_ndof * s.b_temp * s.boltzmann : 0.0;  // npt.py:738-746
     double ekin = s.ekin;
@@ -294,7 +364,7 @@ static __device__ void baro_b(MDState &s) {
 static __device__ void econs_update(MDState &s) {
     double corr = 0.0;
     const double kb = s.boltzmann;
-    if (s.has_thermo && s.thermo_kind == 1) corr += s.be_corr;
+    if (s.has_thermo && s.thermo_kind != 0) corr += s.be_corr;  // Berendsen / CSVR: accumulated (1 - scale^2) ekin
     if (s.has_thermo && s.thermo_kind == 0) {  // nvt.py:453-458
         const double kt = kb * s.ch_temp;
         double a = 0.0, p = 0.0;

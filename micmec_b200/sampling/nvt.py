@@ -132,14 +132,23 @@ class LangevinThermostat(_HostThermostat):
 
 
 class CSVRThermostat(_HostThermostat):
-    """Canonical sampling through stochastic velocity rescaling (nvt.py:221-274)."""
+    """Canonical sampling through stochastic velocity rescaling (nvt.py:221-274).  Host-driven by default for small systems
+    (NumPy stream, the reference's trajectory reproduced); with ``device=True`` (default from 4096 nodes on, when it is the
+    only Verlet hook) the single velocity scale per step is drawn and applied on the device (Philox stream, chi-square by
+    Marsaglia-Tsang instead of ``ndof - 1`` explicit normal deviates): same distribution, statistical parity."""
 
     name = "CSVR"
     kind = "stochastic"
     sets_ndof = True
+    device_threshold = 4096
 
-    def __init__(self, temp, start=0, timecon=100 * femtosecond):
+    def __init__(self, temp, start=0, timecon=100 * femtosecond, device=None):
         _HostThermostat.__init__(self, temp, start, 1, timecon)
+        self.device = device
+        self.seed = None
+
+    def wants_device(self, nnodes):
+        return bool(self.device) if self.device is not None else nnodes >= self.device_threshold
 
     def init(self, iterative):
         _HostThermostat.init(self, iterative)

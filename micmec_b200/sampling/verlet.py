@@ -171,7 +171,7 @@ class VerletIntegrator(Iterative):
     def _native_setup(self):
         """Return (part, thermostat, barostat) when the step can stay on the device, else None."""
         from ..pes.mmff import ForcePartMechanical
-        from .nvt import NHCThermostat, LangevinThermostat, BerendsenThermostat
+        from .nvt import NHCThermostat, LangevinThermostat, BerendsenThermostat, CSVRThermostat
         from .npt import MTKBarostat, TBCombination
 
         parts = getattr(self.mmf, "parts", None)
@@ -182,7 +182,7 @@ class VerletIntegrator(Iterative):
         if len(vhooks) > 1:
             return None
         for hook in vhooks:
-            if isinstance(hook, LangevinThermostat) and hook.start == 0 and getattr(parts[0], "slab", None) is None \
+            if isinstance(hook, (LangevinThermostat, CSVRThermostat)) and hook.start == 0 and getattr(parts[0], "slab", None) is None \
                     and hook.wants_device(self.pos.shape[0]):
                 thermo = hook  # device-resident Langevin thermostat (k_langevin)
                 continue
@@ -222,11 +222,15 @@ class VerletIntegrator(Iterative):
         desc.ndof = float(self.ndof)
         desc.time0, desc.counter0 = float(self.time), int(self.counter)
         self._langevin = self._berendsen = None
-        if thermo is not None and thermo.name == "Berendsen":
+        if thermo is not None and thermo.name in ("Berendsen", "CSVR"):  # one velocity scale per step from the scalar kernel
             self._berendsen, thermo = thermo, None
             self._thermo = None
-            desc.has_thermo, desc.thermo_kind, desc.chain_length = 1, 1, 0
+            desc.has_thermo, desc.thermo_kind, desc.chain_length = 1, (1 if self._berendsen.name == "Berendsen" else 2), 0
             desc.thermo_temp, desc.thermo_timecon = self._berendsen.temp, self._berendsen.timecon
+            if self._berendsen.name == "CSVR":
+                if self._berendsen.seed is None:
+                    self._berendsen.seed = int(np.random.randint(0, 2 ** 31 - 1)) * 2654435761 + 12345
+                desc.langevin_seed = self._berendsen.seed & (2 ** 64 - 1)
         if thermo is not None and not hasattr(thermo, "chain"):  # LangevinThermostat in device mode
             self._langevin, thermo = thermo, None
             self._thermo = None

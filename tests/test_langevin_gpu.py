@@ -81,3 +81,46 @@ def test_canonical_temperature_and_conserved_quantity():
     assert abs(np.mean(z ** 4) - 3.0) <= 0.25  # normal kurtosis
     assert abs(verlet.econs - econs0) <= 2e-2 * verlet.ekin, (verlet.econs, econs0, verlet.ekin)
     assert abs(thermo.econs_correction) > 0.0
+
+
+def test_device_csvr_thermostat_samples_the_canonical_kinetic_energy():
+    """CSVRThermostat(device=True): the stochastic velocity scale is drawn on the device (Philox; chi-square by
+    Marsaglia-Tsang).  Canonical ensemble of the kinetic energy: <T> = 300 K and var(T) / <T>^2 = 2 / ndof; the conserved
+    quantity (etot + sum (1 - alpha^2) ekin) drifts only by the integrator's error; one seed -> one trajectory."""
+    from micmec_b200.system import System
+    from micmec_b200.celltypes import TYPE_FCU
+    from micmec_b200.pes.mmff import MicMecForceField, ForcePartMechanical
+    from micmec_b200.sampling.verlet import VerletIntegrator
+    from micmec_b200.sampling.nvt import CSVRThermostat
+    from micmec_b200.units import femtosecond, boltzmann
+
+    def build(seed):
+        rng = np.random.default_rng(4)
+        system = System.periodic_grid((16, 16, 15), TYPE_FCU, explicit=False)
+        system.pos[:] = system.pos + 0.2 * rng.standard_normal(system.pos.shape)
+        mmf = MicMecForceField(system, [ForcePartMechanical(system, structured=True)])
+        vel0 = rng.standard_normal(system.pos.shape) * np.sqrt(boltzmann * 300.0 / system.masses)[:, None]
+        np.random.seed(seed)
+        thermo = CSVRThermostat(300.0, timecon=50 * femtosecond, device=True)
+        verlet = VerletIntegrator(mmf, timestep=10 * femtosecond, hooks=[thermo], vel0=vel0)
+        assert verlet.device_mode
+        return verlet, thermo
+
+    a, ta = build(5)
+    b, _ = build(5)
+    a.run(20)
+    b.run(20)
+    assert np.array_equal(a.vel, b.vel) and ta.seed is not None
+    a.run(80)
+    econs0 = a.econs
+    temps = []
+    for _ in range(150):
+        a.run(8)
+        temps.append(a.temp)
+    temps = np.array(temps)
+    ndof = float(a.ndof)
+    assert abs(temps.mean() - 300.0) <= 0.01 * 300.0, temps.mean()
+    ratio = temps.std() / (300.0 * np.sqrt(2.0 / ndof))
+    assert 0.6 <= ratio <= 1.6, ratio
+    assert abs(a.econs - econs0) <= 2e-2 * a.ekin, (a.econs, econs0, a.ekin)
+    assert abs(ta.econs_correction) > 0.0
