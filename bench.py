@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="tuning: planes per block along z")
     ap.add_argument("--wrap", type=int, default=-1, help="tuning: 0 = k_march2 reads the periodic images from the ghost nodes")
+    ap.add_argument("--plan", type=int, default=-1, help="tuning: 0 = uniform chunk length for every tile (no two-class block schedule)")
     ap.add_argument("--tail-in-kernel", type=int, default=-1, help="tuning: 1 = the last block of a marching launch runs the tail")
     ap.add_argument("--tail", type=int, default=-1, help="tuning: 0 = reduction / exchange / scalar algebra in their own launches")
     ap.add_argument("--march2", type=int, default=-1, help="tuning: 0 = keep the general kernel k_march for the one-type grids too")
@@ -337,7 +338,7 @@ def main():
         part = ForcePartMechanical(system, model=args.model, device=local_rank, slab=layout.slab_arg())
     if args.march2 >= 0:
         _lib.check(lib.mm_set_option(part.handle, b"march2", args.march2))
-    for name, val in (("wrap_on_load", args.wrap), ("tail", args.tail), ("tail_in_kernel", args.tail_in_kernel)):
+    for name, val in (("wrap_on_load", args.wrap), ("tail", args.tail), ("tail_in_kernel", args.tail_in_kernel), ("plan", args.plan)):
         if val >= 0:
             _lib.check(lib.mm_set_option(part.handle, name.encode(), val))
     if args.chunk:
@@ -363,7 +364,8 @@ def main():
     assert verlet.device_mode
     opt = lambda name: int(lib.mm_get_option(part.handle, name))
     tiling = {"kernel": "k_march2" if opt(b"march2") == 1 else "k_march", "rows_per_thread": opt(b"rows_per_thread"),
-              "warps": opt(b"tile_rows"), "chunk_planes": opt(b"chunk"), "blocks": opt(b"blocks"),
+              "warps": opt(b"tile_rows"), "shortest_chunk_planes": opt(b"chunk"), "blocks": opt(b"blocks"),
+              "schedule_efficiency": opt(b"plan_efficiency_permille") / 1000.0,
               "images_on_load": opt(b"wrap_on_load"), "tail": {0: "separate reduction / scalar / halo launches", 1: "one tail launch", 2: "in the marching kernel"}[opt(b"tail")]}
     md = verlet._md
 

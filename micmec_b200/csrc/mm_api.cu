@@ -416,6 +416,13 @@ int mm_set_option(mm_handle *h, const char *name, int64_t value) {
         MM_CUDA(cudaStreamSynchronize(h->stream));
         return sg_retile(h, 0);
     }
+    if (strcmp(name, "plan") == 0) {
+        h->sg.plan_two_class = value ? 1 : 0;
+        if (!h->sg.d_sc) return MM_OK;
+        MM_CUDA(cudaSetDevice(h->device));
+        MM_CUDA(cudaStreamSynchronize(h->stream));
+        return sg_retile(h, 0);
+    }
     if (strcmp(name, "tail_in_kernel") == 0) {
         h->sg.tail_in_kernel = value ? 1 : 0;
         return MM_OK;
@@ -433,6 +440,8 @@ int64_t mm_get_option(const mm_handle *h, const char *name) {
     if (strcmp(name, "rows_per_thread") == 0) return h->sg.march2 ? h->sg.rpt : 1;
     if (strcmp(name, "march2") == 0) return h->sg.march2;
     if (strcmp(name, "mass_uniform") == 0) return h->sg.mass_uniform;
+    if (strcmp(name, "plan_efficiency_permille") == 0)  // perfect balance / simulated makespan of the block schedule
+        return h->sg.plan_cost > 0.0 ? (int64_t)(1000.0 * h->sg.plan_ideal / h->sg.plan_cost) : -1;
     if (strcmp(name, "tail") == 0) return sg_tail_ok(h) ? (h->sg.tail_in_kernel ? 2 : 1) : 0;
     if (strcmp(name, "wrap_on_load") == 0) return h->sg.wrap_on_load;
     return -1;

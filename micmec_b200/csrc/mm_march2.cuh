@@ -178,10 +178,15 @@ k_march2(const __grid_constant__ SState Pc, const __grid_constant__ MarchArgs a,
     // thread = RPT node columns (k, l0 + r) = cell columns with those origin vertices.  k = -1 / k = nx and l = -1 / l = ny
     // are the periodic images of the last / first column and row: edge tiles stage them separately (see stage_issue) and
     // `off` points the thread at the right copy.  Rows or columns beyond are never owned; what they read is finite.
-    const int k = blockIdx.x * OX + lane - 1, l0 = blockIdx.y * OY + w * RPT - 1;
+    // work item of this block: tile (bx, by) and the plane range [c0, c1) it owns.  Items come from a table built on the host
+    // (sg_plan_items): tiles do not all get the same number of chunks - whole columns first, the remainder of the tiles cut
+    // into short pieces that fill the last round of the SMs
+    const int4 item = a.items[blockIdx.x];
+    const int bx = item.x, by = item.y;
+    const int k = bx * OX + lane - 1, l0 = by * OY + w * RPT - 1;
     // WRAP = false: the images are read from the ghost nodes of the padded arrays instead (kept current by sg_halo)
-    const bool hx0 = WRAP && blockIdx.x == 0, hx1 = WRAP && blockIdx.x == gridDim.x - 1;
-    const bool hy0 = WRAP && blockIdx.y == 0, hy1 = WRAP && blockIdx.y == gridDim.y - 1;
+    const bool hx0 = WRAP && bx == 0, hx1 = WRAP && bx == a.ntx - 1;
+    const bool hy0 = WRAP && by == 0, hy1 = WRAP && by == a.nty - 1;
     const bool edge = hx0 || hx1 || hy0 || hy1;
     const int hmask = (hx0 ? 1 : 0) | (hx1 ? 2 : 0) | (hy0 ? 4 : 0) | (hy1 ? 8 : 0);
     const int ex0 = (nx + 1) & 1;  // element of node nx-1 inside its (even-aligned) 2-column box; node 0 is element 0 of its box
@@ -227,8 +232,7 @@ k_march2(const __grid_constant__ SState Pc, const __grid_constant__ MarchArgs a,
     const int wm = (w > 0) ? w - 1 : w;
 
     const unsigned plane = (unsigned)nxp * (unsigned)(ny + 2);
-    const int c0 = 1 + blockIdx.z * a.chunk;
-    const int c1 = min(c0 + a.chunk, a.nzl + 1);
+    const int c0 = item.z, c1 = item.w;
     // element index of node (k, l0) in array plane p (rows r follow at + r nxp); only dereferenced where owned
     unsigned idx = ((unsigned)(c0 - 1) * (ny + 2) + (unsigned)(l0 + 1)) * nxp + (unsigned)(k + kGhostX);
 
@@ -295,7 +299,7 @@ k_march2(const __grid_constant__ SState Pc, const __grid_constant__ MarchArgs a,
         if (lane == 0) {
             const unsigned bar = smem_u32(&s_full[st]);
             mbar_arrive_expect(bar, w < NF ? my_bytes : 0u);
-            const int bx0 = (int)(blockIdx.x * OX), by0 = (int)(blockIdx.y * OY);
+            const int bx0 = bx * OX, by0 = by * OY;
             for (int f = w; f < NF; f += TY) {
                 const unsigned fb = smem_u32(s_stage) + (st * kStageDoubles + f * FS) * 8u;
                 tma_load_3d(fb, &maps.in[f], bx0, by0, q, bar);
@@ -691,7 +695,7 @@ k_march2(const __grid_constant__ SState Pc, const __grid_constant__ MarchArgs a,
         double s = 0.0;
 #pragma unroll
         for (int u = 0; u < TY; u++) s += red[u][lane];
-        const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        const int bid = blockIdx.x;
         a.partials[(size_t)bid * kRedSlots + lane] = s;
     }
     if (a.tail.enabled) {
@@ -699,7 +703,7 @@ k_march2(const __grid_constant__ SState Pc, const __grid_constant__ MarchArgs a,
         // arrays are consumed by the NEXT launch.  A fence by every thread would wait for the block's whole store queue to
         // drain at the end of every block (measured: +10 us per launch).  The exception are the boundary planes a slab stores
         // into its neighbours' memory: they must have landed before the tail's exchange tells the neighbours so.
-        const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+        const int nblocks = gridDim.x;
         if (a.fused && a.tail.nranks > 1 && (c0 == 1 || c1 == a.nzl + 1)) {
             __threadfence_system();
             __syncthreads();

@@ -21,7 +21,10 @@
 // Apron cells are recomputed by neighbouring blocks (tile 32 x TY threads -> 30 x (TY-2) owned nodes): the price of
 // never materialising per-cell data.  DESIGN.md discusses the trade-off and the measured numbers.  The kernel itself
 // lives in mm_march.cuh; this file holds the layout conversions, halo planes and the launch logic.
+#include <algorithm>
 #include <cstring>
+#include <functional>
+#include <queue>
 #include <vector>
 
 #include "mm_internal.h"
@@ -386,6 +389,10 @@ static int sg_tile_rows_total(const SGrid &g) { return g.march2 ? g.rpt * g.tile
 
 int sg_blocks(const mm_handle *h, dim3 &grid) {
     const SGrid &g = h->sg;
+    if (g.march2 && g.nitems > 0) {  // one block per work item (sg_plan_items)
+        grid = dim3((unsigned)g.nitems, 1, 1);
+        return g.nitems;
+    }
     const int ox = TX - 2, oy = sg_tile_rows_total(g) - 2;
     grid = dim3((g.nx + ox - 1) / ox, (g.ny + oy - 1) / oy, (g.nzl + g.chunk - 1) / g.chunk);
     return (int)(grid.x * grid.y * grid.z);
@@ -414,6 +421,109 @@ static int sg_pick_chunk(const mm_handle *h) {
     return best;
 }
 
+// ---- work items of k_march2 ----------------------------------------------------------------------------------------------
+// A uniform chunk length leaves the last round of the SMs partly empty (256^3 on 8 GPUs: 171 tiles x 4 chunks = 684 blocks of
+// 10 plane iterations = 4.6 rounds on 148 SMs, 50 iterations against 39 with perfect balance).  The planner splits the
+// tiles into two classes - class A: the first TA tiles, nA chunks each (long blocks, dispatched first); class B: the
+// rest, nB >= nA chunks each (short blocks that fill the tail) - and picks (TA, nA, nB) by simulating the block scheduler
+// (blocks go, in index order, to the SM that becomes free first; a block costs (planes + 2) x weight plane iterations; edge
+// tiles weigh more when they fetch the periodic images themselves).
+static double plan_makespan(const std::vector<double> &costs, int nsm) {
+    std::priority_queue<double, std::vector<double>, std::greater<double>> sms;
+    for (int i = 0; i < nsm; i++) sms.push(0.0);
+    double last = 0.0;
+    for (double c : costs) {
+        const double t = sms.top() + c;
+        sms.pop();
+        sms.push(t);
+        last = std::max(last, t);
+    }
+    return last;
+}
+
+static int sg_plan_items(mm_handle *h, int chunk_override) {
+    SGrid &g = h->sg;
+    const int ox = TX - 2, oy = sg_tile_rows_total(g) - 2;
+    const int ntx = (g.nx + ox - 1) / ox, nty = (g.ny + oy - 1) / oy, T = ntx * nty, P = g.nzl, S = h->num_sms;
+    struct Tile {
+        int bx, by;
+        double w;
+    };
+    std::vector<Tile> tiles;
+    // Without images on load all tiles weigh the same and keep the natural order (x fastest: blocks that run side by side
+    // are neighbours in the grid and share their apron rows in L2).  With images on load the heavier edge tiles go last,
+    // into class B, where their extra cost is spread over short chunks (N = 2: 0.789 ms against 0.817 in natural order).
+    for (int pass = 0; pass < (g.wrap_on_load ? 2 : 1); pass++)
+        for (int by = 0; by < nty; by++)
+            for (int bx = 0; bx < ntx; bx++) {
+                const bool edge = bx == 0 || by == 0 || bx == ntx - 1 || by == nty - 1;
+                if (g.wrap_on_load && edge != (pass == 1)) continue;
+                tiles.push_back({bx, by, (edge && g.wrap_on_load) ? 1.2 : 1.0});
+            }
+    auto build = [&](int TA, int nA, int nB, std::vector<int4> *items, std::vector<double> &costs) {
+        costs.clear();
+        if (items) items->clear();
+        for (int cls = 0; cls < 2; cls++) {
+            const int t0 = cls == 0 ? 0 : TA, t1 = cls == 0 ? TA : T, n = cls == 0 ? nA : nB;
+            for (int c = 0; c < n; c++)  // chunk-major: the n pieces of a tile are spread over the dispatch order
+                for (int t = t0; t < t1; t++) {
+                    const int lo = 1 + (int)((int64_t)P * c / n), hi = 1 + (int)((int64_t)P * (c + 1) / n);
+                    if (hi <= lo) continue;
+                    costs.push_back((hi - lo + 2) * tiles[t].w);
+                    if (items) items->push_back(make_int4(tiles[t].bx, tiles[t].by, lo, hi));
+                }
+        }
+    };
+    int bTA = 0, bnA = 1, bnB = 1;
+    double best = -1.0;
+    std::vector<double> costs;
+    if (chunk_override > 0 || !g.plan_two_class) {  // uniform chunks (tuning / A-B): the given length or the cost model's
+        const int chunk = chunk_override > 0 ? chunk_override : sg_pick_chunk(h);
+        bnA = bnB = (P + chunk - 1) / chunk;
+        bTA = 0;
+    } else {
+        const int nmax = std::max(1, P / 2);
+        static const int cand[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 64};
+        for (int nA : cand) {
+            if (nA > nmax || nA > 16) break;
+            for (int nB : cand) {
+                if (nB < nA) continue;
+                if (nB > nmax || (int64_t)T * nB > 16384) break;
+                for (int TA = 0; TA <= T; TA = (TA == T) ? T + 1 : std::min(T, TA + S)) {
+                    if (nA == nB && TA != 0) continue;  // the uniform schedule once
+                    build(TA, nA, nB, nullptr, costs);
+                    const double m = plan_makespan(costs, S);
+                    if (best < 0.0 || m < best * (1.0 - 1e-9) || (m <= best * (1.0 + 1e-9) && (int64_t)TA * nA + (int64_t)(T - TA) * nB < (int64_t)bTA * bnA + (int64_t)(T - bTA) * bnB)) {
+                        best = m;
+                        bTA = TA;
+                        bnA = nA;
+                        bnB = nB;
+                    }
+                }
+            }
+        }
+    }
+    std::vector<int4> items;
+    build(bTA, bnA, bnB, &items, costs);
+    g.plan_cost = plan_makespan(costs, S);
+    double total = 0.0;
+    for (const Tile &t : tiles) total += (double)P * t.w;
+    g.plan_ideal = total / S;
+    g.ntx = ntx;
+    g.nty = nty;
+    g.nitems = (int)items.size();
+    g.chunk = (P + bnB - 1) / bnB;
+    if (g.nitems > g.nitems_alloc) {
+        if (g.d_items) cudaFree(g.d_items);
+        g.d_items = nullptr;
+        MM_CUDA(cudaMalloc(&g.d_items, sizeof(int4) * (size_t)g.nitems));
+        g.nitems_alloc = g.nitems;
+    }
+    MM_CUDA(cudaMemcpyAsync(g.d_items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice, h->stream));
+    MM_CUDA(cudaStreamSynchronize(h->stream));  // `items` is a local
+    return MM_OK;
+}
+
 // (re)derive everything that depends on the tile shape: kernel family, tensor maps, chunk, number of block partials
 int sg_retile(mm_handle *h, int chunk_override) {
     SGrid &g = h->sg;
@@ -431,7 +541,12 @@ int sg_retile(mm_handle *h, int chunk_override) {
     // nodes per GPU on, the ghost-fill launch is cheaper than the image copies of the edge tiles (measured on one GPU,
     // profiles/r02/z: 64^3 NPT 0.092 vs 0.099 ms, 128^3 0.316 vs 0.337, 160^3 0.460 vs 0.440, 256^3 1.437 vs 1.406)
     g.wrap_on_load = g.wrap_wanted >= 0 ? g.wrap_wanted : ((h->slab_count > 1 || h->nnodes <= 128 * 128 * 128) ? 1 : 0);
+    g.nitems = 0;
     g.chunk = chunk_override > 0 ? chunk_override : sg_pick_chunk(h);
+    if (g.march2) {
+        const int rc = sg_plan_items(h, chunk_override);
+        if (rc != MM_OK) return rc;
+    }
     dim3 grid;
     const int nb = sg_blocks(h, grid);
     if (nb > g.nblocks_alloc) {
@@ -514,6 +629,9 @@ void sg_free(mm_handle *h) {
     cudaFree(g.d_sp);
     cudaFree(g.d_tail_counter);
     g.d_tail_counter = nullptr;
+    cudaFree(g.d_items);
+    g.d_items = nullptr;
+    g.nitems = g.nitems_alloc = 0;
     cudaFree(g.d_partials);
     if (g.h_sc) cudaFreeHost(g.h_sc);
     g.active = 0;
@@ -685,6 +803,9 @@ static void fill_args(mm_handle *h, MarchArgs &a) {
     a.minv = g.minv;
     a.type = g.type;
     a.mass = g.mass;
+    a.items = g.d_items;
+    a.ntx = g.ntx;
+    a.nty = g.nty;
     a.sc = g.d_sc;
     a.spg = g.d_sp;
     a.partials = g.d_partials;

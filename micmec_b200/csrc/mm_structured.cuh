@@ -63,6 +63,10 @@ struct SGrid {
     CUtensorMap tm_x[2][3], tm_v[2][3], tm_g[2][3], tm_m, tm_minv;  // load descriptors of the arrays above
     CUtensorMap tw_x[2][3], tw_v[2][3], tw_g[2][3];                 // ... with the 2-column box of k_march2's image columns
     unsigned int *d_tail_counter = nullptr;                         // k_march2 tail: blocks finished
+    int4 *d_items = nullptr;                                        // k_march2 work items (sg_plan_items)
+    int nitems = 0, nitems_alloc = 0, ntx = 0, nty = 0;
+    int plan_two_class = 1;                                         // option "plan": 0 = uniform chunks for every tile
+    double plan_cost = 0.0, plan_ideal = 0.0;                       // simulated makespan / perfect balance, in plane iterations
     int tma_ok = 0;                 // descriptors encoded (driver entry point available, pitch constraints met)
     // fused halo (see MarchArgs): where the z neighbours' copies of this slab's arrays live (own block when there is one
     // slab), their plane counts, and what the last marching launch already delivered
@@ -145,6 +149,8 @@ struct MarchArgs {
     double wrap_lo, wrap_hi;
     int fused;
     double mass;  // k_march2: the uniform node mass
+    const int4 *items;  // k_march2: work items (tile x, tile y, first owned plane, one past the last), one per block
+    int ntx, nty;       // ... and the number of tiles along x / y
     TailArgs tail;
     const StepConsts *sc;
     const SParams *spg;  // the constants once more in global memory (pinned register copies are loaded from here)

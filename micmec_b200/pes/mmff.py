@@ -132,7 +132,7 @@ class ForcePartMechanical(ForcePart):
         if structured is not None:
             _lib.check(self._lib.mm_set_option(self._handle, b"structured", int(bool(structured))))
         # kernel selection / tuning knobs, e.g. MICMEC_B200_MARCH2=0
-        for opt in ("march2", "wrap_on_load", "tail", "tail_in_kernel"):
+        for opt in ("march2", "wrap_on_load", "tail", "tail_in_kernel", "plan"):
             env = os.environ.get("MICMEC_B200_" + opt.upper())
             if env is not None:
                 _lib.check(self._lib.mm_set_option(self._handle, opt.encode(), int(env)))
