@@ -115,8 +115,15 @@ int mm_synchronize(mm_handle *h);
  * the gpos accumulation of the structured path; "profile" 1 = bracket every force kernel with CUDA events */
 int mm_set_option(mm_handle *h, const char *name, int64_t value);
 /* read back a setting or a derived launch parameter: "structured" (1 = the structured-grid kernels are active),
- * "chunk" (planes per block along z), "rows_per_thread", "tile_rows", "blocks", "mass_uniform"; -1 for unknown names */
+ * "chunk" (planes per block along z; the shortest class with the two-class schedule), "rows_per_thread", "tile_rows",
+ * "blocks", "mass_uniform", "march2", "tail", "wrap_on_load", "plan_efficiency_permille"; -1 for unknown names */
 int64_t mm_get_option(const mm_handle *h, const char *name);
+/* The block schedule of the marching kernel for ntx x nty tiles of `planes` owned planes on nsm SMs, without a device (no
+ * counterpart in the reference: introspection for tests and tuning).  items: [capacity][4] = tile x, tile y, first owned
+ * plane (from 1), one past the last, in dispatch order (may be NULL to query *nitems); cost / ideal: simulated makespan and
+ * perfect balance in plane iterations.  uniform_chunk > 0: equal chunks of that length instead of the two-class plan. */
+int mm_plan_schedule(int ntx, int nty, int planes, int nsm, int images_on_load, int uniform_chunk, int32_t *items, int64_t capacity,
+                     int64_t *nitems, double *cost, double *ideal);
 /* with "profile" on: launches timed since the last call and their summed device time (ms), separately for
  * [0] force-only kernels and [1] fused kick-drift-force-kick kernels; synchronises the stream and resets the counters */
 int mm_profile(mm_handle *h, int64_t nlaunch[2], double total_ms[2]);

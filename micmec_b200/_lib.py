@@ -25,7 +25,7 @@ S_VTENS, S_PTENS, S_NFORCE, S_CE_N, S_COUNT = 16, 25, 34, 35, 40
 EXPORTS = [
     "mm_create", "mm_destroy", "mm_last_error", "mm_version", "mm_device_ok", "mm_set_pos", "mm_set_rvecs",
     "mm_compute", "mm_get_cell_cache", "mm_launch_count", "mm_device_ptr", "mm_set_stream", "mm_synchronize",
-    "mm_set_option", "mm_get_option", "mm_profile", "mm_batched_eigh", "mm_qn_create", "mm_qn_destroy", "mm_qn_sweep", "mm_qn_get", "mm_set_rvecs_batch", "mm_get_replica_results", "mm_comm_unique_id", "mm_comm_init", "mm_comm_destroy", "mm_comm_mode", "mm_domain", "mm_md_create", "mm_md_destroy", "mm_md_init", "mm_md_set_state", "mm_md_run", "mm_md_get_state",
+    "mm_set_option", "mm_get_option", "mm_plan_schedule", "mm_profile", "mm_batched_eigh", "mm_qn_create", "mm_qn_destroy", "mm_qn_sweep", "mm_qn_get", "mm_set_rvecs_batch", "mm_get_replica_results", "mm_comm_unique_id", "mm_comm_init", "mm_comm_destroy", "mm_comm_mode", "mm_domain", "mm_md_create", "mm_md_destroy", "mm_md_init", "mm_md_set_state", "mm_md_run", "mm_md_get_state",
     "mm_md_scalars",
 ]
 
@@ -113,6 +113,7 @@ def load():
     lib.mm_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.mm_get_option.argtypes = [vp, ctypes.c_char_p]
     lib.mm_get_option.restype = i64
+    lib.mm_plan_schedule.argtypes = [ctypes.c_int] * 6 + [vp, i64, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.mm_profile.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(dbl)]  # int64[2], double[2]
     lib.mm_set_rvecs_batch.argtypes = [vp, vp]
     lib.mm_get_replica_results.argtypes = [vp, vp, vp]

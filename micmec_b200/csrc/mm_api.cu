@@ -447,6 +447,24 @@ int64_t mm_get_option(const mm_handle *h, const char *name) {
     return -1;
 }
 
+int mm_plan_schedule(int ntx, int nty, int planes, int nsm, int images_on_load, int uniform_chunk, int32_t *items, int64_t capacity,
+                     int64_t *nitems, double *cost, double *ideal) {
+    if (ntx < 1 || nty < 1 || planes < 1 || nsm < 1 || !nitems) return invalid("mm_plan_schedule: bad argument");
+    std::vector<int4> v;
+    sg_plan_schedule(ntx, nty, planes, nsm, images_on_load, uniform_chunk, v, cost, ideal, nullptr);
+    *nitems = (int64_t)v.size();
+    if (items) {
+        if (capacity < (int64_t)v.size()) return invalid("mm_plan_schedule: items buffer too small");
+        for (size_t i = 0; i < v.size(); i++) {
+            items[4 * i + 0] = v[i].x;
+            items[4 * i + 1] = v[i].y;
+            items[4 * i + 2] = v[i].z;
+            items[4 * i + 3] = v[i].w;
+        }
+    }
+    return MM_OK;
+}
+
 int mm_profile(mm_handle *h, int64_t *nlaunch, double *total_ms) {
     if (!h || !nlaunch || !total_ms) return invalid("mm_profile: null argument");
     MM_CUDA(cudaSetDevice(h->device));

@@ -114,7 +114,7 @@ bool sg_eligible(const mm_handle *h);
 int sg_setup(mm_handle *h);
 void sg_free(mm_handle *h);
 int sg_write_consts(mm_handle *h, const double *rvecs9, double dt);
-int sg_halo(mm_handle *h, bool pos, bool vel, bool grad);
+int sg_halo(mm_handle *h, bool pos, bool vel, bool grad, const double *rv_src = nullptr, cudaStream_t st = nullptr);
 int sg_pos_from_aos(mm_handle *h, const double *d_aos);
 int sg_vel_from_aos(mm_handle *h, const double *d_aos);
 int sg_mass_from_aos(mm_handle *h, const double *d_masses);
@@ -132,6 +132,8 @@ int sg_set_chunk(mm_handle *h, int chunk);
 int sg_set_rpt(mm_handle *h, int rpt);
 int sg_set_march2(mm_handle *h, int on);
 int sg_retile(mm_handle *h, int chunk_override);
+void sg_plan_schedule(int ntx, int nty, int P, int S, int images_on_load, int uniform_chunk, std::vector<int4> &items,
+                      double *cost, double *ideal, int *chunk_b);
 
 // ---- mm_comm.cu ---------------------------------------------------------------------------------------------
 int comm_halo(mm_handle *h, double **fields, int nfields, int npos);

@@ -17,6 +17,7 @@
 // velocities anyway (the kick).  That removes every velocity-only pass of the reference
 // (vel *= factor, vel = vel @ rot_mat, _compute_ekin).
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -337,6 +338,14 @@ struct mm_md {
     int64_t glaunches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t steps_done = 0;
     int use_graphs = 1;
+    // Lean steps on the ghost-node path (one GPU, grids above 128^3 nodes): the x / y ghost fill that follows a marching launch
+    // and the scalar kernel that follows it too do not depend on each other and can run side by side (ghost fill on a side
+    // stream, fork / join by events, captured into the step graphs).  Measured (profiles/r02, calls ag / ah): 1.3547-1.3615 ms
+    // per NPT step at 256^3 against 1.3568-1.3589 in stream order - the two kernels are ~12-15 us each and the extra graph
+    // edges cost what the overlap saves.  Off; MICMEC_B200_HALO_OVERLAP=1 turns it on.
+    int overlap_halo = 0;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace mm {
@@ -535,13 +544,35 @@ static int md_step_structured(mm_md *md, bool full, bool own_pre, bool merge_nex
         return MM_OK;
     }
     if (full) sg_export(md, true, false, md->d_posold);  // posold of verlet.py:158-161 (a full step always has own_pre)
+    // Ghost fill beside the scalar kernel (lean steps, one slab).  The ghost positions are shifted by the domain vectors of the
+    // frame the positions were stored in; where the scalar kernel running alongside is about to change StepConsts::rv, the
+    // caller names a source that is already final (see the two call sites).
+    const bool beside = md->overlap_halo && !full && !lang && h->slab_count <= 1 && md->side != nullptr;
+    auto halo_beside = [&](bool pos, bool vel, bool grad, const double *rv_src, unsigned ops, int nbd_) {
+        MM_CUDA(cudaEventRecord(md->ev_fork, h->stream));
+        MM_CUDA(cudaStreamWaitEvent(md->side, md->ev_fork, 0));
+        int rc = sg_halo(h, pos, vel, grad, rv_src, md->side);
+        if (rc != MM_OK) return rc;
+        MM_CUDA(cudaEventRecord(md->ev_join, md->side));
+        rc = scalar_launch(md, ops, nb, nb, nbd_);
+        MM_CUDA(cudaStreamWaitEvent(h->stream, md->ev_join, 0));
+        return rc;
+    };
     if (baro) {
         if (own_pre) scalar_launch(md, OP_BARO_A, 0, 0, 0);
         // npt.py:683-707: rotate the positions (all pending rotations at once) and evaluate; the rotated positions are
         // written back so that the fused step below needs no rotation; the gradient is what its first kick uses
         sg_force(h, true, 2);
-        scalar_launch(md, OP_POS_WRITTEN | OP_TAKE_FORCE | OP_BARO_B | (thermo ? OP_THERMO : 0u), nb, nb, 0);
-        sg_halo(h, true, false, true);  // after OP_POS_WRITTEN: the halo shift uses the new stored frame
+        const unsigned ops_b = OP_POS_WRITTEN | OP_TAKE_FORCE | OP_BARO_B | (thermo ? OP_THERMO : 0u);
+        if (beside) {
+            // the rotated positions are in the true frame: their domain vectors are the handle's device copy, final since the
+            // barostat's first half (OP_BARO_A / OP_NEXT_BARO_A) - exactly what OP_POS_WRITTEN is about to put into StepConsts
+            const int rc = halo_beside(true, false, true, h->d_rvecs, ops_b, 0);
+            if (rc != MM_OK) return rc;
+        } else {
+            scalar_launch(md, ops_b, nb, nb, 0);
+            sg_halo(h, true, false, true);  // after OP_POS_WRITTEN: the halo shift uses the new stored frame
+        }
     } else if (thermo) {
         if (own_pre) scalar_launch(md, OP_THERMO, 0, 0, 0);
     } else if (lang && own_pre) {
@@ -552,7 +583,11 @@ static int md_step_structured(mm_md *md, bool full, bool own_pre, bool merge_nex
     sg_step(h, !baro, baro ? 2 : (thermo ? 1 : 0), !full);
     unsigned ops = OP_RESET_MVEL | OP_POS_WRITTEN | OP_TAKE_FORCE | OP_TAKE_KIN | post_thermo;
     int nbd = 0;
-    if (!baro) {
+    if (!baro && beside) {
+        // rv_stored is unchanged without a barostat: the scalar kernel rewrites StepConsts::rv with the same values
+        const int rc = halo_beside(true, true, true, nullptr, ops | OP_ECONS | OP_ADVANCE | OP_PROPS | next_op, 0);
+        if (rc != MM_OK) return rc;
+    } else if (!baro) {
         sg_halo(h, true, true, true);  // rv_stored is unchanged without a barostat: safe before the scalar kernel
         if (full) {
             sg_export(md, true, false, h->d_pos);
@@ -567,8 +602,15 @@ static int md_step_structured(mm_md *md, bool full, bool own_pre, bool merge_nex
         }
         scalar_launch(md, ops | OP_ECONS | OP_ADVANCE | OP_PROPS | next_op, nb, nb, nbd);
     } else {
-        scalar_launch(md, ops | OP_BARO_A, nb, nb, 0);
-        sg_halo(h, true, true, false);  // after OP_POS_WRITTEN: the halo shift must use the new stored frame
+        if (beside) {
+            // the drifted positions stay in the frame of the launch before (true frame, cell unchanged by the Verlet step):
+            // OP_POS_WRITTEN rewrites StepConsts::rv with the values it holds; OP_BARO_A then moves on the handle's copy only
+            const int rc = halo_beside(true, true, false, nullptr, ops | OP_BARO_A, 0);
+            if (rc != MM_OK) return rc;
+        } else {
+            scalar_launch(md, ops | OP_BARO_A, nb, nb, 0);
+            sg_halo(h, true, true, false);  // after OP_POS_WRITTEN: the halo shift must use the new stored frame
+        }
         // npt.py:683-707 again; this rotation stays pending until the next step.  The gradient of this call is only
         // read by compute_properties (rmsd_gpos) and by trajectory output: lean steps evaluate energy + virial alone
         sg_force(h, full, 1, !full);
@@ -602,6 +644,9 @@ int mm_md_destroy(mm_md *md) {
     if (md->h_state) cudaFreeHost(md->h_state);
     for (int i = 0; i < 8; i++)
         if (md->gexec[i]) cudaGraphExecDestroy(md->gexec[i]);
+    if (md->side) cudaStreamDestroy(md->side);
+    if (md->ev_fork) cudaEventDestroy(md->ev_fork);
+    if (md->ev_join) cudaEventDestroy(md->ev_join);
     delete md;
     return MM_OK;
 }
@@ -655,6 +700,10 @@ int mm_md_create(mm_handle *h, const mm_md_desc *desc, mm_md **out) {
     MM_TRY(cudaMalloc(&md->d_pdelta, sizeof(double) * kMaxRedBlocks * kRedSlots));
     MM_TRY(cudaMalloc(&md->d_plang, sizeof(double) * kMaxRedBlocks * kRedSlots));
     MM_TRY(cudaHostAlloc(&md->h_state, sizeof(MDState), cudaHostAllocDefault));
+    MM_TRY(cudaStreamCreateWithFlags(&md->side, cudaStreamNonBlocking));
+    MM_TRY(cudaEventCreateWithFlags(&md->ev_fork, cudaEventDisableTiming));
+    MM_TRY(cudaEventCreateWithFlags(&md->ev_join, cudaEventDisableTiming));
+    if (const char *e = getenv("MICMEC_B200_HALO_OVERLAP")) md->overlap_halo = atoi(e) != 0;  // A/B switch (profiles/r02)
 #undef MM_TRY
     *out = md;
     return MM_OK;

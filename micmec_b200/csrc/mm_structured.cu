@@ -44,6 +44,7 @@ struct HaloArgs {
     double *f[9];
     int nfields;
     int npos;  // the first npos fields are position components 0, 1, 2
+    const double *rv;  // the nine domain-vector components of the stored frame (StepConsts::rv unless the caller knows better)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
@@ -71,7 +72,7 @@ k_halo_xy(const __grid_constant__ HaloArgs h, int nx, int ny, int nxp, int64_t p
         const int64_t dst = ((int64_t)p * (ny + 2) + l + 1) * nxp + k + kGhostX;
         const int64_t src = ((int64_t)p * (ny + 2) + (l - qy * ny) + 1) * nxp + (k - qx * nx) + kGhostX;
         for (int f = 0; f < h.nfields; f++) {
-            const double shift = (f < h.npos) ? qx * sc->rv[f] + qy * sc->rv[3 + f] : 0.0;
+            const double shift = (f < h.npos) ? qx * h.rv[f] + qy * h.rv[3 + f] : 0.0;
             h.f[f][dst] = h.f[f][src] + shift;
         }
     }
@@ -100,10 +101,15 @@ k_halo_xy_fused(const __grid_constant__ HaloArgs h, int nx, int ny, int nxp, int
         const int qx = (k < 0) ? -1 : (k >= nx ? 1 : 0), qy = (l < 0) ? -1 : (l >= ny ? 1 : 0);
         const int64_t dst = ((int64_t)p * (ny + 2) + l + 1) * nxp + k + kGhostX;
         const int64_t src = ((int64_t)p * (ny + 2) + (l - qy * ny) + 1) * nxp + (k - qx * nx) + kGhostX;
-        for (int f = 0; f < h.nfields; f++) {
-            const double shift = (f < h.npos) ? qx * sc->rv[f] + qy * sc->rv[3 + f] : 0.0;
-            h.f[f][dst] = (remote ? __ldcg(h.f[f] + src) : h.f[f][src]) + shift;
-        }
+        // all loads first: the fields may alias as far as the compiler knows, and nine dependent load -> store round trips
+        // are most of this kernel's time
+        double val[9];
+#pragma unroll
+        for (int f = 0; f < 9; f++)
+            if (f < h.nfields) val[f] = remote ? __ldcg(h.f[f] + src) : h.f[f][src];
+#pragma unroll
+        for (int f = 0; f < 9; f++)
+            if (f < h.nfields) h.f[f][dst] = val[f] + ((f < h.npos) ? qx * h.rv[f] + qy * h.rv[3 + f] : 0.0);
     };
     // exchanges completed so far: read by every block before the last one to finish can advance it
     const unsigned long long want = flags ? ld_acquire_sys_u64(epoch) + 1 : 0ull;
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(256)
 k_halo(const __grid_constant__ HaloArgs h, int64_t plane, int nzl, const StepConsts *sc) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x) {
         for (int f = 0; f < h.nfields; f++) {
-            const double c = (f < h.npos) ? sc->rv[6 + f] : 0.0;
+            const double c = (f < h.npos) ? h.rv[6 + f] : 0.0;
             h.f[f][i] = h.f[f][(int64_t)nzl * plane + i] - c;
             h.f[f][(int64_t)(nzl + 1) * plane + i] = h.f[f][plane + i] + c;
         }
@@ -441,10 +447,12 @@ static double plan_makespan(const std::vector<double> &costs, int nsm) {
     return last;
 }
 
-static int sg_plan_items(mm_handle *h, int chunk_override) {
-    SGrid &g = h->sg;
-    const int ox = TX - 2, oy = sg_tile_rows_total(g) - 2;
-    const int ntx = (g.nx + ox - 1) / ox, nty = (g.ny + oy - 1) / oy, T = ntx * nty, P = g.nzl, S = h->num_sms;
+// Pure host part (also exported as mm_plan_schedule for the CPU tests): ntx x nty tiles, P owned planes, S SMs.
+// uniform_chunk > 0 asks for equal chunks of that length for every tile.  Returns the items (tile x, tile y, first owned
+// plane, one past the last; planes count from 1) in dispatch order.
+void sg_plan_schedule(int ntx, int nty, int P, int S, int images_on_load, int uniform_chunk, std::vector<int4> &items,
+                      double *cost, double *ideal, int *chunk_b) {
+    const int T = ntx * nty;
     struct Tile {
         int bx, by;
         double w;
@@ -453,16 +461,16 @@ static int sg_plan_items(mm_handle *h, int chunk_override) {
     // Without images on load all tiles weigh the same and keep the natural order (x fastest: blocks that run side by side
     // are neighbours in the grid and share their apron rows in L2).  With images on load the heavier edge tiles go last,
     // into class B, where their extra cost is spread over short chunks (N = 2: 0.789 ms against 0.817 in natural order).
-    for (int pass = 0; pass < (g.wrap_on_load ? 2 : 1); pass++)
+    for (int pass = 0; pass < (images_on_load ? 2 : 1); pass++)
         for (int by = 0; by < nty; by++)
             for (int bx = 0; bx < ntx; bx++) {
                 const bool edge = bx == 0 || by == 0 || bx == ntx - 1 || by == nty - 1;
-                if (g.wrap_on_load && edge != (pass == 1)) continue;
-                tiles.push_back({bx, by, (edge && g.wrap_on_load) ? 1.2 : 1.0});
+                if (images_on_load && edge != (pass == 1)) continue;
+                tiles.push_back({bx, by, (edge && images_on_load) ? 1.2 : 1.0});
             }
-    auto build = [&](int TA, int nA, int nB, std::vector<int4> *items, std::vector<double> &costs) {
+    auto build = [&](int TA, int nA, int nB, std::vector<int4> *out, std::vector<double> &costs) {
         costs.clear();
-        if (items) items->clear();
+        if (out) out->clear();
         for (int cls = 0; cls < 2; cls++) {
             const int t0 = cls == 0 ? 0 : TA, t1 = cls == 0 ? TA : T, n = cls == 0 ? nA : nB;
             for (int c = 0; c < n; c++)  // chunk-major: the n pieces of a tile are spread over the dispatch order
@@ -470,16 +478,15 @@ static int sg_plan_items(mm_handle *h, int chunk_override) {
                     const int lo = 1 + (int)((int64_t)P * c / n), hi = 1 + (int)((int64_t)P * (c + 1) / n);
                     if (hi <= lo) continue;
                     costs.push_back((hi - lo + 2) * tiles[t].w);
-                    if (items) items->push_back(make_int4(tiles[t].bx, tiles[t].by, lo, hi));
+                    if (out) out->push_back(make_int4(tiles[t].bx, tiles[t].by, lo, hi));
                 }
         }
     };
     int bTA = 0, bnA = 1, bnB = 1;
     double best = -1.0;
     std::vector<double> costs;
-    if (chunk_override > 0 || !g.plan_two_class) {  // uniform chunks (tuning / A-B): the given length or the cost model's
-        const int chunk = chunk_override > 0 ? chunk_override : sg_pick_chunk(h);
-        bnA = bnB = (P + chunk - 1) / chunk;
+    if (uniform_chunk > 0) {
+        bnA = bnB = (P + uniform_chunk - 1) / uniform_chunk;
         bTA = 0;
     } else {
         const int nmax = std::max(1, P / 2);
@@ -503,16 +510,25 @@ static int sg_plan_items(mm_handle *h, int chunk_override) {
             }
         }
     }
-    std::vector<int4> items;
     build(bTA, bnA, bnB, &items, costs);
-    g.plan_cost = plan_makespan(costs, S);
+    if (cost) *cost = plan_makespan(costs, S);
     double total = 0.0;
     for (const Tile &t : tiles) total += (double)P * t.w;
-    g.plan_ideal = total / S;
+    if (ideal) *ideal = total / S;
+    if (chunk_b) *chunk_b = (P + bnB - 1) / bnB;
+}
+
+static int sg_plan_items(mm_handle *h, int chunk_override) {
+    SGrid &g = h->sg;
+    const int ox = TX - 2, oy = sg_tile_rows_total(g) - 2;
+    const int ntx = (g.nx + ox - 1) / ox, nty = (g.ny + oy - 1) / oy;
+    // uniform chunks (tuning / A-B): the given length or the cost model's
+    const int uniform = chunk_override > 0 ? chunk_override : (g.plan_two_class ? 0 : sg_pick_chunk(h));
+    std::vector<int4> items;
+    sg_plan_schedule(ntx, nty, g.nzl, h->num_sms, g.wrap_on_load, uniform, items, &g.plan_cost, &g.plan_ideal, &g.chunk);
     g.ntx = ntx;
     g.nty = nty;
     g.nitems = (int)items.size();
-    g.chunk = (P + bnB - 1) / bnB;
     if (g.nitems > g.nitems_alloc) {
         if (g.d_items) cudaFree(g.d_items);
         g.d_items = nullptr;
@@ -651,11 +667,15 @@ int sg_write_consts(mm_handle *h, const double *rvecs9, double dt) {
     return MM_OK;
 }
 
-int sg_halo(mm_handle *h, bool pos, bool vel, bool grad) {
+// rv_src: device pointer to the nine domain-vector components the position ghosts are shifted by (default: StepConsts::rv);
+// st: launch on this stream instead of the handle's (single slab only: the MD step runs the ghost fill beside its scalar kernel)
+int sg_halo(mm_handle *h, bool pos, bool vel, bool grad, const double *rv_src, cudaStream_t st) {
     SGrid &g = h->sg;
+    cudaStream_t stream = st ? st : h->stream;
     HaloArgs ha;
     ha.nfields = 0;
     ha.npos = 0;
+    ha.rv = rv_src ? rv_src : reinterpret_cast<const double *>(g.d_sc) + offsetof(StepConsts, rv) / sizeof(double);
     if (pos) {
         for (int d = 0; d < 3; d++) ha.f[ha.nfields++] = g.x[g.cx][d];
         ha.npos = 3;
@@ -671,29 +691,29 @@ int sg_halo(mm_handle *h, bool pos, bool vel, bool grad) {
         g.fused_mask = 0;
         if (delivered) {
             if (h->slab_count > 1 && !g.tail_done) {
-                k_halo_handshake<<<1, 32, 0, h->stream>>>(g.halo_flags, g.halo_epoch, g.nb_flag[0], g.nb_flag[1]);
+                k_halo_handshake<<<1, 32, 0, stream>>>(g.halo_flags, g.halo_epoch, g.nb_flag[0], g.nb_flag[1]);
                 h->launches++;
             }
             g.tail_done = 0;
             return MM_OK;
         }
         if (h->slab_count > 1) return comm_halo(h, ha.f, ha.nfields, ha.npos);
-        k_halo<<<grid_for(h, g.plane, 256), 256, 0, h->stream>>>(ha, g.plane, g.nzl, g.d_sc);
+        k_halo<<<grid_for(h, g.plane, 256), 256, 0, stream>>>(ha, g.plane, g.nzl, g.d_sc);
         h->launches++;
         return MM_OK;
     }
     if (g.fused && g.fused_mask == mask) {  // the marching kernel delivered the boundary planes itself
         g.fused_mask = 0;
-        k_halo_xy_fused<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * (g.nzl + 2), 256), 256, 0, h->stream>>>(
+        k_halo_xy_fused<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * (g.nzl + 2), 256), 256, 0, stream>>>(
             ha, g.nx, g.ny, g.nxp, g.nzl, g.d_sc, g.halo_flags, g.halo_epoch, g.halo_done, g.nb_flag[0], g.nb_flag[1]);
         h->launches++;
         return MM_OK;
     }
     g.fused_mask = 0;
-    k_halo_xy<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * g.nzl, 256), 256, 0, h->stream>>>(ha, g.nx, g.ny, g.nxp, g.plane, g.nzl, g.d_sc);
+    k_halo_xy<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * g.nzl, 256), 256, 0, stream>>>(ha, g.nx, g.ny, g.nxp, g.plane, g.nzl, g.d_sc);
     h->launches++;
     if (h->slab_count > 1) return comm_halo(h, ha.f, ha.nfields, ha.npos);  // (padded) planes travel between the slabs
-    k_halo<<<grid_for(h, g.plane, 256), 256, 0, h->stream>>>(ha, g.plane, g.nzl, g.d_sc);
+    k_halo<<<grid_for(h, g.plane, 256), 256, 0, stream>>>(ha, g.plane, g.nzl, g.d_sc);
     h->launches++;
     return MM_OK;
 }
@@ -703,6 +723,7 @@ int sg_halo_mass(mm_handle *h) {
     HaloArgs ha;
     ha.nfields = 2;
     ha.npos = 0;
+    ha.rv = nullptr;  // no position fields: never read
     ha.f[0] = g.m;
     ha.f[1] = g.minv;
     k_halo_xy<<<grid_for(h, (int64_t)(2 * (g.nx + 2) + 2 * g.ny) * g.nzl, 256), 256, 0, h->stream>>>(ha, g.nx, g.ny, g.nxp, g.plane, g.nzl, g.d_sc);
