@@ -1,5 +1,4 @@
 """CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every declared symbol."""
-import ctypes
 import os
 import re
 
