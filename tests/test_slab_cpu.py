@@ -111,3 +111,18 @@ def test_oracle_grid_builder_matches_the_package_generator():
         assert np.array_equal(arrays["shift"], orc.cell_shifts(system.grid, system.surrounding_nodes, True))
         assert np.array_equal(pos, system.pos) and np.array_equal(masses, system.masses)
         assert np.array_equal(rvecs, np.array(system.domain.rvecs))
+
+
+def test_bench_clock_sampler_degrades_without_nvml():
+    """bench.py samples SM clocks through NVML during the timed region; NVML is initialised in the constructor (outside
+    the region).  Where there is no driver (this container) the sampler must neither raise nor hang, and say why it
+    has no samples."""
+    import bench
+
+    sampler = bench.ClockSampler(0)
+    sampler.start()
+    out = sampler.stop()
+    assert set(out) == {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
+    if out["samples"] == 0:
+        assert out["sm_mhz"] is None
+        assert any(r.startswith("unavailable") for r in out["reasons"])
